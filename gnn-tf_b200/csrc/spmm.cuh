@@ -1,0 +1,29 @@
+// Epilogue descriptor shared by the SpMM kernels and the APPNP drivers.
+#pragma once
+#include "common.cuh"
+
+namespace gnntf {
+
+struct Epilogue {
+    float s;             // scale on (A·B)[m]
+    const float* H0;     // + t * H0[m]            (NULL = none)
+    int64_t ldh;
+    float t;
+    const uint8_t* keep; // feature keep-mask, dense [n_rows, F] (NULL = none)
+    float p_scale;
+    int act;             // GNNTF_ACT_*
+    float* C;            // output (NULL = not written)
+    int64_t ldc;
+    float* ACC;          // ACC[m] = (acc_init ? 0 : ACC[m]) + u*B[m] + w*out[m]   (NULL = none)
+    int64_t ldacc;
+    float u, w;
+    int acc_init;
+    const float* B;      // the dense operand (for the u*B[m] term)
+    int64_t ldb;
+    int F;
+};
+
+int spmm_dispatch(const gnntf_csr_t* A, const float* B, int64_t ldb, Epilogue epi, cudaStream_t st);
+int validate_csr(const gnntf_csr_t* A);
+
+}  // namespace gnntf

@@ -1,0 +1,197 @@
+"""Differentiable host wrappers of the native propagation ops (the "registered gradient" of the
+reference's TF ops, here as ``torch.autograd.Function``s over the C-ABI).
+
+* :func:`sparse_dense_matmul` — ``tf.sparse.sparse_dense_matmul`` (filter.py:19, gcn.py:88) and its
+  ``adjoint_a`` gradient (trainable.py:78).  No gradient flows into the adjacency values (they
+  depend on no variable; the reference computes that branch and discards it).
+* :func:`appnp_step` — one fused ``PPRIteration.__forward__`` (filter.py:17-22).
+* :func:`appnp_propagate` — K fused iterations (filter.py:34-35 under layered.py:52-55) with the
+  fused backward of SURVEY.md Appendix C.
+"""
+from __future__ import annotations
+
+import ctypes
+
+import torch
+
+from . import _native as nat
+from .sparse import NormalizedAdjacency, SparseAdjacency
+
+
+def _as_norm(adj):
+    if isinstance(adj, SparseAdjacency):  # raw graph2adj output used directly: normalized="none"
+        return adj.normalized("none")
+    if not isinstance(adj, NormalizedAdjacency):
+        raise Exception("expected the adjacency returned by graph2adj / get_adjacency")
+    return adj
+
+
+def _dense(x, n_rows=None):
+    if x.dtype != torch.float32 or not x.is_cuda:
+        raise Exception("features must be a float32 CUDA tensor")
+    if x.dim() != 2:
+        raise Exception("features must be a 2-D [nodes, features] tensor")
+    if x.stride(1) != 1 or x.stride(0) < x.shape[1]:
+        x = x.contiguous()
+    return x
+
+
+def _ld(x):
+    return x.stride(0) if x.shape[0] > 1 else max(x.shape[1], x.stride(0))
+
+
+def spmm_raw(csr_struct, n_rows, B, out=None):
+    """C = A·B on raw tensors (no autograd)."""
+    L = nat.lib()
+    B = _dense(B)
+    F = B.shape[1]
+    C = out if out is not None else torch.empty((n_rows, F), dtype=torch.float32, device=B.device)
+    nat.check(L.gnntf_spmm_f32(ctypes.byref(csr_struct), nat.ptr(B), _ld(B), nat.ptr(C), _ld(C), F,
+                               nat.stream_ptr()), "spmm")
+    return C
+
+
+class _SpMM(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, adj, H):
+        ctx.adj = adj
+        return spmm_raw(adj.struct(H.shape[1]), adj.base.n, H)
+
+    @staticmethod
+    def backward(ctx, g):
+        adj = ctx.adj
+        if not ctx.needs_input_grad[1]:
+            return None, None  # e.g. the constant feature matrix of the first GCN layer
+        g = _dense(g)
+        return None, spmm_raw(adj.struct_T(g.shape[1]), adj.base.n, g)
+
+
+def sparse_dense_matmul(adj, H):
+    """Drop-in for ``tf.sparse.sparse_dense_matmul(adj, H)``."""
+    adj = _as_norm(adj)
+    H = _dense(H)
+    if H.shape[0] != adj.base.n:
+        raise Exception(f"dimension mismatch: adjacency is {adj.dense_shape}, features have {H.shape[0]} rows")
+    return _SpMM.apply(adj, H)
+
+
+def _step_raw(struct, H_in, H0, alpha, feat_keep=None, p_scale=1.0, act=nat.ACT_IDENTITY, out=None):
+    L = nat.lib()
+    F = H_in.shape[1]
+    ld = _ld(H_in)
+    assert _ld(H0) == ld
+    out = out if out is not None else torch.empty_like(H_in)
+    nat.check(L.gnntf_appnp_step_f32(ctypes.byref(struct), nat.ptr(H_in), nat.ptr(H0), nat.ptr(out), ld, F,
+                                     float(alpha), nat.ptr(feat_keep), float(p_scale), int(act),
+                                     nat.stream_ptr()), "appnp_step")
+    return out
+
+
+class _Step(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, adj, H, H0, alpha, feat_keep, p_scale, relu):
+        H, H0 = H.contiguous(), H0.contiguous()
+        out = _step_raw(adj.struct(H.shape[1]), H, H0, alpha, feat_keep, p_scale,
+                        nat.ACT_RELU if relu else nat.ACT_IDENTITY)
+        ctx.adj, ctx.alpha, ctx.p_scale, ctx.relu = adj, alpha, p_scale, relu
+        ctx.save_for_backward(feat_keep if feat_keep is not None else torch.empty(0), out if relu else torch.empty(0))
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        keep, out = ctx.saved_tensors
+        g = g.contiguous()
+        if ctx.relu:
+            g = g * (out > 0)
+        if keep.numel():
+            g = g * keep.to(g.dtype) * ctx.p_scale
+        dH = spmm_raw(ctx.adj.struct_T(g.shape[1]), ctx.adj.base.n, g).mul_(1.0 - ctx.alpha) \
+            if ctx.needs_input_grad[1] else None
+        dH0 = g * ctx.alpha if ctx.needs_input_grad[2] else None
+        return None, dH, dH0, None, None, None, None
+
+
+def appnp_step(adj, H, H0, alpha, feat_keep=None, p_feat=0.0, relu=False):
+    """``act(dropout((1-a)·Â·H + a·H0))`` in one kernel (filter.py:19-22)."""
+    adj = _as_norm(adj)
+    p_scale = 1.0 / (1.0 - p_feat) if feat_keep is not None else 1.0
+    if feat_keep is not None:
+        feat_keep = feat_keep.to(torch.uint8).contiguous()
+    return _Step.apply(adj, _dense(H), _dense(H0), float(alpha), feat_keep, p_scale, bool(relu))
+
+
+def _struct_array(structs):
+    arr = (nat.CsrStruct * len(structs))()
+    for i, s in enumerate(structs):
+        arr[i] = s
+    return arr
+
+
+def propagate_raw(adjs, H0, alpha, K, out=None, scratch=None):
+    """K fused steps on raw tensors.  ``adjs``: one NormalizedAdjacency (eval: shared by all steps)
+    or a list of K (training: one edge mask per step, filter.py:18)."""
+    L = nat.lib()
+    F, ld = H0.shape[1], _ld(H0)
+    out = out if out is not None else torch.empty_like(H0)
+    if scratch is None and K > 1:
+        scratch = torch.empty_like(H0)
+    if isinstance(adjs, (list, tuple)):
+        arr = _struct_array([a.struct(F) for a in adjs])
+        nat.check(L.gnntf_appnp_propagate_multi_f32(arr, K, nat.ptr(H0), nat.ptr(out), nat.ptr(scratch), ld, F,
+                                                    float(alpha), nat.stream_ptr()), "appnp_propagate_multi")
+    else:
+        s = adjs.struct(F)
+        nat.check(L.gnntf_appnp_propagate_f32(ctypes.byref(s), nat.ptr(H0), nat.ptr(out), nat.ptr(scratch), ld, F,
+                                              float(alpha), K, nat.stream_ptr()), "appnp_propagate")
+    return out
+
+
+class _Propagate(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, adjs, H0, alpha, K):
+        H0 = H0.contiguous()
+        ctx.adjs, ctx.alpha, ctx.K = adjs, alpha, K
+        return propagate_raw(adjs, H0, alpha, K)
+
+    @staticmethod
+    def backward(ctx, g):
+        L = nat.lib()
+        g = g.contiguous()
+        F, ld, K = g.shape[1], _ld(g), ctx.K
+        adjs = ctx.adjs if isinstance(ctx.adjs, (list, tuple)) else [ctx.adjs] * K
+        arr = _struct_array([a.struct_T(F) for a in adjs])
+        dH0 = torch.empty_like(g)
+        scratch = torch.empty((2,) + tuple(g.shape), dtype=g.dtype, device=g.device) if K > 1 else None
+        nat.check(L.gnntf_appnp_propagate_bwd_f32(arr, K, nat.ptr(g), nat.ptr(dH0), nat.ptr(scratch), ld, F,
+                                                  float(ctx.alpha), nat.stream_ptr()), "appnp_propagate_bwd")
+        return None, dH0, None, None
+
+
+def appnp_propagate(adjs, H0, alpha=0.1, iterations=10):
+    """``H ← (1−a)·Â·H + a·H0`` K times, starting from ``H = H0``; differentiable w.r.t. ``H0``."""
+    if isinstance(adjs, (list, tuple)):
+        adjs = [_as_norm(a) for a in adjs]
+        if len(adjs) != iterations:
+            raise Exception("one adjacency per iteration is required")
+    else:
+        adjs = _as_norm(adjs)
+    return _Propagate.apply(adjs, _dense(H0), float(alpha), int(iterations))
+
+
+def appnp_propagate_host(adj, H0_host, alpha=0.1, iterations=10, out_host=None, bufs=None):
+    """End-to-end form with HOST feature buffers (pinned for full speed): H2D copy, K fused steps,
+    D2H copy, all on the current stream; returns the host tensor after synchronising."""
+    L = nat.lib()
+    adj = _as_norm(adj)
+    n, F = H0_host.shape
+    if bufs is None:
+        bufs = [torch.empty((n, F), dtype=torch.float32, device="cuda") for _ in range(3)]
+    if out_host is None:
+        out_host = torch.empty((n, F), dtype=torch.float32, pin_memory=True)
+    s = adj.struct(F)
+    nat.check(L.gnntf_appnp_propagate_host_f32(ctypes.byref(s), nat.ptr(H0_host), nat.ptr(out_host),
+                                               nat.ptr(bufs[0]), nat.ptr(bufs[1]), nat.ptr(bufs[2]), F, F,
+                                               float(alpha), int(iterations), nat.stream_ptr()),
+              "appnp_propagate_host")
+    torch.cuda.current_stream().synchronize()
+    return out_host

@@ -1,0 +1,199 @@
+/* gnntf_b200.h — C-ABI of the B200-native sparse adjacency propagation path of gnntf.
+ *
+ * The reference (MKLab-ITI/gnn-tf) has no FFI of its own: its hot path is a chain of stock
+ * TensorFlow ops issued from Python.  Each entry point below replaces one of those call sites
+ * (file:line relative to the reference root) and is what a TF custom op (tf_op/gnntf_ops.cc,
+ * loaded with tf.load_op_library) or the ctypes host shim (gnntf/_native.py) binds:
+ *
+ *   gnntf_csr_build*        gnntf/core/gnn/graph_manipulation.py:24-31  graph2adj (symmetrise by
+ *                           appending the reversed list, duplicates kept) -> COO .indices/.values
+ *                           + the stable-by-row CSR view the kernels consume
+ *   gnntf_normalize_f32     gnntf/core/nn/layered.py:47-50   sparse_dropout  (explicit keep-mask)
+ *                           gnntf/core/gnn/gnn.py:36-50      get_adjacency   (colsum, D, row*col scale)
+ *   gnntf_spmm_f32          tf.sparse.sparse_dense_matmul at filter.py:19, gcn.py:24,48,88,104,131
+ *                           (and its adjoint_a=True gradient, trainable.py:78)
+ *   gnntf_appnp_step_f32    gnntf/core/gnn/architectures/filter.py:19-22  SpMM + teleport axpy
+ *                           (+ feature dropout + relu) in one pass
+ *   gnntf_appnp_propagate*  the K PPRIteration layers, filter.py:34-35 under layered.py:52-55
+ *   gnntf_appnp_propagate_bwd_f32   their VJP (tape.gradient, trainable.py:78)
+ *
+ * Conventions.  Every pointer is a DEVICE pointer unless its name ends in _host.  The library
+ * is stateless and re-entrant: the caller owns every buffer, workspace sizes are queried first,
+ * nothing is allocated and nothing synchronises (all work is enqueued on `stream`, a
+ * cudaStream_t passed as void*; 0 = legacy default stream).  Return value: 0 = OK, < 0 = one of
+ * the GNNTF_E_* argument errors, > 0 = a cudaError_t.  No exception crosses the ABI.
+ * Index widths: caller-facing COO indices are int64 (tf.SparseTensor.indices); the internal CSR
+ * is int32, so nnz must be < 2^31 (the largest BASELINE config, R-MAT 1e9 edges, is 2.0e9).
+ * Dense matrices are row-major fp32 with an explicit leading dimension (in floats).
+ */
+#ifndef GNNTF_B200_H
+#define GNNTF_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GNNTF_ABI_VERSION 1
+
+#define GNNTF_OK 0
+#define GNNTF_E_NULL (-1)      /* a required pointer is NULL */
+#define GNNTF_E_SIZE (-2)      /* negative size, nnz >= 2^31, or ld < F */
+#define GNNTF_E_MODE (-3)      /* "Invalid matrix normalization" (gnn.py:46-47) or bad enum */
+#define GNNTF_E_WORKSPACE (-4) /* workspace too small */
+#define GNNTF_E_ALIGN (-5)     /* pointer not 4-byte aligned */
+
+/* normalized= of GNN.get_adjacency (gnn.py:36) */
+#define GNNTF_NORM_SYMMETRIC 0 /* D = 1/sqrt(colsum); v*D[row]*D[col]   gnn.py:40-42 */
+#define GNNTF_NORM_BIPARTITE 1 /* D = 1/colsum;       v*D[row]          gnn.py:43-45 */
+#define GNNTF_NORM_NONE 2
+
+/* add_eye= of GNN.get_adjacency (gnn.py:38-39, 48-49) */
+#define GNNTF_EYE_NONE 0
+#define GNNTF_EYE_BEFORE 1
+#define GNNTF_EYE_AFTER 2
+
+/* activation fused in the step epilogue (PPRIteration activation, filter.py:22) */
+#define GNNTF_ACT_IDENTITY 0
+#define GNNTF_ACT_RELU 1
+
+int gnntf_abi_version(void);
+const char* gnntf_status_str(int code);
+
+/* ------------------------------------------------------------------------------------------
+ * CSR view of a (normalised) adjacency.  Built by gnntf_csr_build + gnntf_spmm_plan_*.
+ * Rows with more than `long_threshold` entries are split into `chunk`-sized pieces that run on
+ * separate warps and are reduced in a fixed order (deterministic, no float atomics).
+ * n_long == 0 means no row is split (then the plan pointers may be NULL).
+ * ---------------------------------------------------------------------------------------- */
+typedef struct gnntf_csr {
+    int64_t n_rows;
+    int64_t nnz;
+    const int32_t* row_ptr; /* [n_rows+1] */
+    const int32_t* col_idx; /* [nnz]      */
+    const float* val;       /* [nnz]      */
+    const int32_t* row_map; /* [n_rows] dense-matrix row that CSR row i reads its teleport term
+                               from and writes to, or NULL = identity.  Lets a row SUBSET (interior /
+                               boundary rows of a shard) run as its own compact CSR. */
+    int32_t long_threshold; /* rows with deg > long_threshold are split; <= 0 disables */
+    int32_t chunk;          /* entries per piece */
+    int32_t n_long;
+    int32_t n_chunks;
+    const int32_t* long_row;         /* [n_long]   row index                       */
+    const int32_t* long_first_chunk; /* [n_long]   first piece of that row         */
+    const int32_t* long_n_chunks;    /* [n_long]   number of pieces                */
+    const int32_t* chunk_row;        /* [n_chunks] row index of the piece          */
+    const int32_t* chunk_begin;      /* [n_chunks] first CSR slot of the piece     */
+    float* partials;                 /* [n_chunks * round_up(F,4)] workspace, or NULL if n_long==0 */
+} gnntf_csr_t;
+
+/* ------------------------------------------------------------------------------------------
+ * (a) graph2adj -> COO + CSR                                   graph_manipulation.py:24-31
+ * edges: int64 [n_edges,2] in graph2indices order (:19-21); weights fp32 [n_edges] or NULL (=1., :27).
+ * nnz = (directed ? 1 : 2)*n_edges + (add_eye ? n : 0).  Slot q of the COO list is
+ *   q <  E          : (u_q, v_q, w_q)
+ *   E <= q < 2E     : (v_{q-E}, u_{q-E}, w_{q-E})      [undirected only, :28-30]
+ *   then n diagonal entries (i,i,1.)                    [add_eye != 0; tf.sparse.eye, gnn.py:39,49]
+ * Outputs: coo_indices int64 [nnz,2] / coo_values fp32 [nnz] (the SparseTensor fields; either may
+ * be NULL), and the CSR obtained by a STABLE sort of that list by row: row_ptr int32 [n+1],
+ * col_idx int32 [nnz], raw_val fp32 [nnz], coo_pos int32 [nnz] (COO slot of each CSR slot).
+ * Indices outside [0,n) are not detected here (the host shim validates).
+ * ---------------------------------------------------------------------------------------- */
+int gnntf_csr_build_ws_bytes(int64_t n, int64_t n_edges, int directed, int add_eye, size_t* bytes);
+int gnntf_csr_build(const int64_t* edges, const float* weights, int64_t n, int64_t n_edges,
+                    int directed, int add_eye, int by_column,
+                    int64_t* coo_indices, float* coo_values,
+                    int32_t* row_ptr, int32_t* col_idx, float* raw_val, int32_t* coo_pos,
+                    void* ws, size_t ws_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * sparse_dropout + get_adjacency on the CSR view            layered.py:47-50, gnn.py:36-50
+ * keep_mask_coo: uint8 [n_graph] in COO order (1 = keep) or NULL (eval mode / p == 0);
+ * scale = fp32(1/(1-p)).  n_graph = nnz without the eye entries; eye_mode says how the trailing
+ * n eye entries (if the CSR was built with add_eye) take part (BEFORE: normalised like any
+ * entry; AFTER: excluded from the degree, value stays 1).  directed != 0 means the COO list has
+ * no appended reverse half, so column sums use float atomics instead of the partner trick.
+ * Outputs: deg [n], dinv [n] (0 where deg == 0, divide_no_nan), norm_val [nnz] (CSR order),
+ * norm_val_T [nnz] or NULL (values of the TRANSPOSED matrix laid on the same CSR structure —
+ * valid for undirected graphs only; equals norm_val when no mask is given),
+ * norm_val_coo [nnz] or NULL (COO order: the .values of the SparseTensor get_adjacency returns).
+ * ---------------------------------------------------------------------------------------- */
+int gnntf_normalize_f32(const int32_t* row_ptr, const int32_t* col_idx, const float* raw_val,
+                        const int32_t* coo_pos, int64_t n, int64_t nnz, int64_t n_graph,
+                        int directed, const uint8_t* keep_mask_coo, float scale, int mode,
+                        int eye_mode, float* deg, float* dinv, float* norm_val, float* norm_val_T,
+                        float* norm_val_coo, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Long-row plan for the SpMM kernels (two calls so the caller can size the arrays).
+ * counts: int32 [2] device = {n_long, n_chunks}.
+ * ---------------------------------------------------------------------------------------- */
+int gnntf_spmm_plan_count(const int32_t* row_ptr, int64_t n_rows, int32_t long_threshold,
+                          int32_t chunk, int32_t* counts, void* stream);
+int gnntf_spmm_plan_fill(const int32_t* row_ptr, int64_t n_rows, int32_t long_threshold,
+                         int32_t chunk, int32_t* counters_ws /* int32[2], zeroed by the call */,
+                         int32_t* long_row, int32_t* long_first_chunk, int32_t* long_n_chunks,
+                         int32_t* chunk_row, int32_t* chunk_begin, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * (b) SpMM   C[n_rows,F] = A · B                  tf.sparse.sparse_dense_matmul (filter.py:19, gcn.py:88)
+ * The backward dB = Aᵀ·dC is the same call on the transposed values (gnntf_normalize_f32's
+ * norm_val_T; identical to A when no edge dropout was applied).  B and C must not alias.
+ * ---------------------------------------------------------------------------------------- */
+int gnntf_spmm_f32(const gnntf_csr_t* A, const float* B, int64_t ldb, float* C, int64_t ldc,
+                   int64_t F, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * (c) one PPRIteration, fused                                          filter.py:19-22
+ *   H_out = act( keep ∘ p_scale ∘ ( (1-alpha)·(A·H_in) + alpha·H0 ) )
+ * feat_keep: uint8 [n_rows, F] (dense, ld = F) or NULL (p_feat == 0, the APPNP default, filter.py:8).
+ * ---------------------------------------------------------------------------------------- */
+int gnntf_appnp_step_f32(const gnntf_csr_t* A, const float* H_in, const float* H0, float* H_out,
+                         int64_t ld, int64_t F, double alpha, const uint8_t* feat_keep,
+                         float p_scale, int activation, void* stream);
+
+/* K fused steps, eval-mode semantics (one adjacency for all steps): H_1 = step(H0) … H_K -> H_out.
+ * scratch: n_rows*ld floats (ping-pong partner of H_out).  H0, H_out, scratch must be distinct. */
+int gnntf_appnp_propagate_f32(const gnntf_csr_t* A, const float* H0, float* H_out, float* scratch,
+                              int64_t ld, int64_t F, double alpha, int K, void* stream);
+
+/* Training-mode forward: step k uses its own adjacency A_k[k] (own edge mask, filter.py:18). */
+int gnntf_appnp_propagate_multi_f32(const gnntf_csr_t* A_k, int K, const float* H0, float* H_out,
+                                    float* scratch, int64_t ld, int64_t F, double alpha, void* stream);
+
+/* VJP of the K-step loop (p_feat = 0, act = identity): given dH_K returns dH0.
+ * AT_k[k] = TRANSPOSED adjacency of step k (pass the same struct K times, or K == n_adj == 1
+ * semantics via gnntf_appnp_propagate_f32 on the transposed matrix, when all steps share one).
+ * For k = K-1..0:  dH0 += alpha·g;  g = (1-alpha)·AT_k[k]·g;  finally dH0 += g.
+ * scratch: 2*n_rows*ld floats.  dHK, dH0, scratch distinct. */
+int gnntf_appnp_propagate_bwd_f32(const gnntf_csr_t* AT_k, int K, const float* dHK, float* dH0,
+                                  float* scratch, int64_t ld, int64_t F, double alpha, void* stream);
+
+/* Same as gnntf_appnp_propagate_f32 but with HOST feature buffers: H0_host (n_rows*F floats,
+ * dense, pinned for full speed) is copied to dev_H0, the K steps run, and dev_out is copied back
+ * to out_host — all enqueued on `stream` (the caller synchronises).  dev_* are device buffers of
+ * n_rows*ld floats each.  This is the end-to-end entry the benchmark's `e2e` leg times. */
+int gnntf_appnp_propagate_host_f32(const gnntf_csr_t* A, const float* H0_host, float* out_host,
+                                   float* dev_H0, float* dev_out, float* dev_scratch, int64_t ld,
+                                   int64_t F, double alpha, int K, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Row-sharded multi-GPU helpers (contiguous node-range split; BASELINE north_star).
+ * Rank r owns rows [lo,hi).  Its local CSR addresses an EXTENDED feature matrix
+ *   H_ext = [ n_local owned rows | n_halo rows received from peers ]
+ * gnntf_csr_localize rewrites global column ids in place: c in [lo,hi) -> c-lo, otherwise
+ * n_local + (rank of c in halo_cols, the sorted distinct remote columns; binary search).
+ * gnntf_halo_pack_f32 gathers the rows a peer needs (send_idx, local row ids) into a dense send
+ * buffer: out[i,:] = H[send_idx[i],:].
+ * ---------------------------------------------------------------------------------------- */
+int gnntf_csr_localize(int32_t* col_idx, int64_t nnz, int64_t lo, int64_t hi,
+                       const int32_t* halo_cols, int64_t n_halo, void* stream);
+int gnntf_halo_pack_f32(const float* H, int64_t ld, const int32_t* send_idx, int64_t n_send,
+                        float* out, int64_t ldo, int64_t F, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GNNTF_B200_H */

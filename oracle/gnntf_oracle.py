@@ -1,0 +1,321 @@
+"""CPU oracle for gnntf's sparse adjacency propagation path.  TEST INFRASTRUCTURE ONLY.
+
+This file is a plain-NumPy restatement of the reference algorithm (MKLab-ITI/gnn-tf,
+``gnntf`` 0.0.20).  It is NOT a product path: only ``tests/``, ``__graft_entry__.smoke()``
+and the ``cpu_baseline`` / ``--impl reference`` legs of ``bench.py`` may import it, and there
+only as the checker or the timed CPU arm.  Nothing under ``gnn-tf_b200/`` imports it.
+
+PARITY UNPINNED.  The reference has no tests, golden vectors or fixtures for this path
+ and its arithmetic lives in TensorFlow, an un-vendored, un-pinned
+dependency (``setup.py:26-28``) that is not installed in this image, so the reference
+cannot be executed here.  The oracle is pinned only against (i) the two known-answer
+tests KAT-1/KAT-2 that SURVEY.md §8c derives by hand from the cited reference lines,
+(ii) independent ``scipy.sparse`` cross-checks, and (iii) its own fp64 twin.  TensorFlow
+semantics assumed (published op behaviour, unverifiable here):
+  * ``tf.sparse.sparse_dense_matmul`` (CPU): ``out[row_i,:] += val_i * B[col_i,:]`` for the
+    COO entries in STORAGE order, fp32 accumulation.
+  * ``tf.sparse.reduce_sum(A, axis=0)``: column sums.
+  * ``tf.math.divide_no_nan(1, x)``: 0 where x == 0.
+  * ``Tensor * SparseTensor`` / ``SparseTensor * Tensor``: the dense operand is broadcast to
+    the sparse operand's [N,N] shape and multiplied onto the stored values (so a [N,1]
+    column scales by ROW, a [N] vector scales by COLUMN).
+  * ``tf.nn.dropout(x, rate)``: ``x * fp32(1/(1-rate))`` where kept, 0 where dropped, one
+    independent draw per element.  TF's Philox stream is not reproducible, so every
+    function here takes an explicit keep-mask.
+
+Every function cites the reference file:line (relative to the reference root) it follows.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+F32 = np.float32
+
+# --------------------------------------------------------------------------------------
+# graph2adj                                                    gnntf/core/gnn/graph_manipulation.py
+# --------------------------------------------------------------------------------------
+
+
+def graph2indices(G):
+    """``graph2indices`` (graph_manipulation.py:19-21): node id = position in ``enumerate(G)``;
+    one ``[id(u), id(v)]`` per ``G.edges()`` entry, in networkx iteration order."""
+    node2id = {u: idx for idx, u in enumerate(G)}
+    return [[node2id[u], node2id[v]] for u, v in G.edges()]
+
+
+def graph2adj(G, directed=False):
+    """``graph2adj`` (graph_manipulation.py:24-31).  Returns ``(indices int64 [nnz,2],
+    values fp32 [nnz], dense_shape)`` — the three fields of the ``tf.sparse.SparseTensor``
+    the reference builds at :31.  Weight attr defaults to 1. (:27); undirected graphs get
+    the reversed edge list APPENDED with the values duplicated (:28-30).  No sort, no
+    coalescing, no self loops added."""
+    indices = graph2indices(G)
+    values = [edge[2].get("weight", 1.) for edge in G.edges(data=True)]
+    n = len(G)
+    return graph2adj_arrays(np.asarray(indices, dtype=np.int64).reshape(-1, 2),
+                            np.asarray(values, dtype=F32), n, directed)
+
+
+def graph2adj_arrays(edges, weights, n, directed=False):
+    """Array-native form of graph_manipulation.py:26-31 for graphs networkx cannot hold:
+    ``edges`` is the ``graph2indices`` list as an int64 [E,2] array, ``weights`` fp32 [E]
+    (``None`` = all 1., the :27 default)."""
+    edges = np.asarray(edges, dtype=np.int64).reshape(-1, 2)
+    E = edges.shape[0]
+    if weights is None:
+        weights = np.ones(E, dtype=F32)
+    weights = np.asarray(weights, dtype=F32)
+    if not directed:
+        indices = np.concatenate([edges, edges[:, ::-1]], axis=0)       # :29
+        values = np.concatenate([weights, weights])                     # :30
+    else:
+        indices, values = edges.copy(), weights.copy()
+    return np.ascontiguousarray(indices), np.ascontiguousarray(values), (int(n), int(n))
+
+
+# --------------------------------------------------------------------------------------
+# sparse_dropout / dropout                                        gnntf/core/nn/layered.py
+# --------------------------------------------------------------------------------------
+
+
+def dropout_scale(rate):
+    """fp32(1/(1-rate)) — the scale ``tf.nn.dropout`` applies to kept elements."""
+    return F32(1.0 / (1.0 - float(rate)))
+
+
+def sparse_dropout(values, rate, keep_mask, training=True):
+    """``Layered.sparse_dropout`` (layered.py:47-50): identity when ``rate == 0`` or in eval
+    mode (:48-49); else ``tf.nn.dropout`` on the nnz value vector (:50), one independent
+    keep decision per COO entry (``keep_mask`` is in COO storage order)."""
+    if rate == 0 or not training:
+        return values
+    keep = np.asarray(keep_mask).astype(bool)
+    return np.where(keep, values.astype(F32) * dropout_scale(rate), F32(0)).astype(F32)
+
+
+def dropout(features, rate, keep_mask, training=True):
+    """``Layered.dropout`` (layered.py:44-45)."""
+    if rate == 0 or not training:
+        return features
+    keep = np.asarray(keep_mask).astype(bool)
+    return np.where(keep, features.astype(F32) * dropout_scale(rate), F32(0)).astype(F32)
+
+
+# --------------------------------------------------------------------------------------
+# GNN.get_adjacency                                                gnntf/core/gnn/gnn.py
+# --------------------------------------------------------------------------------------
+
+
+def column_sums(indices, values, n, dtype=F32):
+    """``tf.sparse.reduce_sum(graph, axis=0)`` (gnn.py:41,44): sum over ROWS, i.e. one sum per
+    column.  Accumulated in storage order in ``dtype``."""
+    deg = np.zeros(n, dtype=dtype)
+    np.add.at(deg, indices[:, 1], values.astype(dtype))
+    return deg
+
+
+def divide_no_nan_recip(x):
+    """``tf.math.divide_no_nan(1., x)``: 1/x, and exactly 0 where x == 0."""
+    out = np.zeros_like(x)
+    nz = x != 0
+    out[nz] = x.dtype.type(1) / x[nz]
+    return out
+
+
+def get_adjacency(indices, values, n, normalized="symmetric", add_eye="none", dtype=F32):
+    """``GNN.get_adjacency`` after the dropout step (gnn.py:38-50); the dropout itself
+    (gnn.py:37) is :func:`sparse_dropout`.  Returns ``(indices, values, D)``.
+
+    symmetric (:40-42):  D = divide_no_nan(1, sqrt(colsum));  v_i <- (v_i * D[row_i]) * D[col_i]
+                         (row-scale op first, then column-scale op: two fp32 roundings).
+    bipartite (:43-45):  D = divide_no_nan(1, colsum);        v_i <- v_i * D[row_i]
+    none:                values unchanged;  anything else raises (:46-47).
+    add_eye "before"/"after" (:38-39, :48-49) appends the N diagonal entries of
+    ``tf.sparse.eye`` (value 1) to the COO list — numerically what ``tf.sparse.add`` yields
+    for every downstream use on this path (SpMM and column sums are linear in the entries).
+    """
+    indices = np.asarray(indices, dtype=np.int64)
+    values = np.asarray(values).astype(dtype)
+    if add_eye == "before":
+        indices, values = _append_eye(indices, values, n)
+    D = None
+    if normalized == "symmetric":
+        D = divide_no_nan_recip(np.sqrt(column_sums(indices, values, n, dtype)))
+        values = (values * D[indices[:, 0]]) * D[indices[:, 1]]
+    elif normalized == "bipartite":
+        D = divide_no_nan_recip(column_sums(indices, values, n, dtype))
+        values = values * D[indices[:, 0]]
+    elif normalized != "none":
+        raise Exception("Invalid matrix normalization")
+    if add_eye == "after":
+        indices, values = _append_eye(indices, values, n)
+    return indices, values.astype(dtype), D
+
+
+def _append_eye(indices, values, n):
+    eye = np.arange(n, dtype=np.int64)
+    return (np.concatenate([indices, np.stack([eye, eye], axis=1)], axis=0),
+            np.concatenate([values, np.ones(n, dtype=values.dtype)]))
+
+
+# --------------------------------------------------------------------------------------
+# SpMM  tf.sparse.sparse_dense_matmul            call sites filter.py:19, gcn.py:24,48,88,104,131
+# --------------------------------------------------------------------------------------
+
+
+def spmm_coo(indices, values, H, n_rows=None, dtype=F32):
+    """``tf.sparse.sparse_dense_matmul(A, H)`` as TF-CPU computes it: a single loop over the
+    COO entries in storage order, ``out[row_i,:] += val_i * H[col_i,:]`` accumulated in
+    ``dtype``.  ``np.add.at`` is unbuffered and applies the updates in index order, so the
+    per-row accumulation order equals TF's."""
+    H = np.asarray(H).astype(dtype)
+    n_rows = H.shape[0] if n_rows is None else n_rows
+    out = np.zeros((n_rows, H.shape[1]), dtype=dtype)
+    contrib = values.astype(dtype)[:, None] * H[indices[:, 1]]
+    np.add.at(out, indices[:, 0], contrib)
+    return out
+
+
+def spmm_coo_T(indices, values, G, n_cols=None, dtype=F32):
+    """Gradient of SpMM w.r.t. the dense operand: ``dH = A^T · dOut`` (TF computes it with
+    ``adjoint_a=True``; triggered at trainable.py:78).  A^T ≠ A whenever edge dropout was
+    active."""
+    return spmm_coo(indices[:, ::-1], values, G, n_rows=n_cols, dtype=dtype)
+
+
+# --------------------------------------------------------------------------------------
+# PPRIteration / APPNP loop                         gnntf/core/gnn/architectures/filter.py
+# --------------------------------------------------------------------------------------
+
+
+def ppr_iteration(indices, norm_values, H, H0, a, feat_keep=None, p_feat=0.0,
+                  training=False, activation=None, dtype=F32):
+    """``PPRIteration.__forward__`` (filter.py:17-22) given the already-normalised adjacency
+    of this iteration (:18): ``propagated = Â·H`` (:19); ``propagated*(1-a) + H0*a`` (:21, two
+    multiplies then an add, each rounded in ``dtype``); feature dropout then activation (:22;
+    defaults p=0 / identity, :8)."""
+    t = np.dtype(dtype).type
+    propagated = spmm_coo(indices, norm_values, H, dtype=dtype)
+    act = propagated * t(1 - a) + np.asarray(H0).astype(dtype) * t(a)
+    act = dropout(act, p_feat, feat_keep, training) if (training and p_feat != 0) else act
+    return activation(act) if activation is not None else act
+
+
+def appnp_propagate(indices, raw_values, n, H0, a=0.1, iterations=10, graph_dropout=0.0,
+                    edge_keep_masks=None, training=False, dtype=F32):
+    """The K ``PPRIteration`` layers APPNP stacks (filter.py:34-35), driven by
+    ``Layered.__call__`` (layered.py:52-55).  Every iteration re-runs ``get_adjacency``
+    (filter.py:18 → gnn.py:36-50); in training mode each draws its OWN edge mask
+    (``edge_keep_masks[k]``, COO order).  ``H0`` is both the start vector and the teleport
+    term (``self.H0.value``, layered.py:79-81).  Returns the list [H_1..H_K]."""
+    H0 = np.asarray(H0).astype(dtype)
+    H, outs = H0, []
+    for k in range(iterations):
+        vals = raw_values
+        if training and graph_dropout != 0:
+            vals = sparse_dropout(raw_values, graph_dropout, edge_keep_masks[k], True)
+        idx, nv, _ = get_adjacency(indices, vals, n, "symmetric", "none", dtype=dtype)
+        H = ppr_iteration(idx, nv, H, H0, a, dtype=dtype)
+        outs.append(H)
+    return outs
+
+
+def appnp_propagate_bwd(indices, norm_values_per_iter, dHK, a=0.1, dtype=F32):
+    """VJP of the K-step loop (derived from filter.py:17-22 with
+    p_feat=0, act=id).  For k = K-1..0: ``dH0 += a·dU_k``; ``dH_k = (1-a)·Â_kᵀ·dU_k`` with
+    ``dU_k = dH_{k+1}``; finally ``dH0 += dH_0`` (H_0 is the same tensor as the teleport
+    term).  ``norm_values_per_iter[k]`` are iteration k's normalised values (their own edge
+    mask).  No gradient flows into Â.  Returns dH0."""
+    t = np.dtype(dtype).type
+    g = np.asarray(dHK).astype(dtype)
+    dH0 = np.zeros_like(g)
+    for k in reversed(range(len(norm_values_per_iter))):
+        dH0 = dH0 + g * t(a)
+        g = spmm_coo_T(indices, norm_values_per_iter[k], g, n_cols=g.shape[0], dtype=dtype) * t(1 - a)
+    return dH0 + g
+
+
+# --------------------------------------------------------------------------------------
+# GCNLayer                                             gnntf/core/gnn/architectures/gcn.py
+# --------------------------------------------------------------------------------------
+
+
+def relu(x):
+    return np.maximum(x, x.dtype.type(0))
+
+
+def gcn_layer(indices, norm_values, X, W, b, activation=relu, feat_keep=None, p_feat=0.0,
+              training=False, dtype=F32):
+    """``GCNLayer.__forward__`` (gcn.py:87-89): aggregate FIRST at the input width
+    (``Â·X``, :88), then ``·W + b``, activation (default relu, :78), dropout (:89)."""
+    Z = spmm_coo(indices, norm_values, X, dtype=dtype)
+    P = Z @ np.asarray(W).astype(dtype) + (np.asarray(b).astype(dtype) if b is not None else 0)
+    Y = activation(P) if activation is not None else P
+    return dropout(Y, p_feat, feat_keep, training) if (training and p_feat != 0) else Y
+
+
+def gcn_forward(indices, raw_values, n, X, weights, biases, dtype=F32):
+    """Eval-mode ``GCN`` forward (gcn.py:108-113): hidden ``GCNLayer``s then the output
+    ``GCNLayer(num_classes)`` which keeps the default relu (:113 → :78).  Eval mode ⇒ both
+    dropouts are identities (layered.py:45,48)."""
+    idx, nv, _ = get_adjacency(indices, raw_values, n, "symmetric", "none", dtype=dtype)
+    H = np.asarray(X).astype(dtype)
+    for W, b in zip(weights, biases):
+        H = gcn_layer(idx, nv, H, W, b, dtype=dtype)
+    return H
+
+
+# --------------------------------------------------------------------------------------
+# Derived CSR view (what the GPU builder must reproduce bit-exactly)
+# --------------------------------------------------------------------------------------
+
+
+def csr_from_coo(indices, n, directed=False):
+    """Stable-by-row CSR of the ``graph2adj`` COO list.  Not a reference function: it is the
+    uniquely defined derived layout the CUDA builder emits, so the oracle states it for the
+    bit-exact index check.  ``coo_pos[p]`` = COO storage position of CSR slot p (stable ⇒
+    within a row, slots keep COO order, which is TF's accumulation order);
+    ``perm_T[p]`` = CSR slot of the transposed partner entry (COO position q±E), defined only
+    for the symmetrised (``directed=False``) list."""
+    indices = np.asarray(indices, dtype=np.int64)
+    nnz = indices.shape[0]
+    coo_pos = np.argsort(indices[:, 0], kind="stable").astype(np.int64)
+    counts = np.bincount(indices[:, 0], minlength=n).astype(np.int64)
+    row_ptr = np.zeros(n + 1, dtype=np.int64)
+    np.cumsum(counts, out=row_ptr[1:])
+    col_idx = indices[coo_pos, 1].astype(np.int32)
+    perm_T = None
+    if not directed:
+        E = nnz // 2
+        inv = np.empty(nnz, dtype=np.int64)
+        inv[coo_pos] = np.arange(nnz, dtype=np.int64)
+        partner = np.where(coo_pos < E, coo_pos + E, coo_pos - E)
+        perm_T = inv[partner]
+    return row_ptr, col_idx, coo_pos, perm_T
+
+
+# --------------------------------------------------------------------------------------
+# Tolerance used by every fp32 parity test (north_star: 1e-5 relative, fp32)
+# --------------------------------------------------------------------------------------
+
+RTOL = 1e-5
+
+
+def assert_close(actual, expected, rtol=RTOL, what=""):
+    """|x−y| ≤ rtol·max(|y|, 0.1·‖y‖∞): 1e-5 relative, with a norm-wise floor for small elements
+    (they are held to 1e-6·‖y‖∞ absolute).  An elementwise relative error is unbounded where the
+    expected value crosses zero, and fp32 rounding noise is ~1e-7·‖y‖∞ per
+    accumulation: the fp32 oracle itself sits 1e-6·‖y‖∞ from its fp64 twin after K=10 steps."""
+    a = np.asarray(actual, dtype=np.float64)
+    e = np.asarray(expected, dtype=np.float64)
+    assert a.shape == e.shape, f"{what}: shape {a.shape} vs {e.shape}"
+    if e.size == 0:
+        return
+    floor = 0.1 * float(np.max(np.abs(e))) if e.size else 0.0
+    bound = rtol * np.maximum(np.abs(e), floor)
+    err = np.abs(a - e)
+    bad = err > bound
+    if bad.any():
+        i = np.unravel_index(np.argmax(err / np.maximum(bound, 1e-300)), e.shape)
+        raise AssertionError(f"{what}: {int(bad.sum())}/{e.size} outside rtol={rtol}; worst at {i}: "
+                             f"{a[i]!r} vs {e[i]!r}")

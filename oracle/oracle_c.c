@@ -1,0 +1,90 @@
+/* CPU oracle (C) for gnntf's sparse adjacency propagation path.  TEST INFRASTRUCTURE ONLY.
+ *
+ * Plain-C restatement of the reference algorithm, used (a) by tests/ as the checker at sizes
+ * where the NumPy oracle is too slow and (b) by bench.py's cpu_baseline / --impl reference
+ * legs as the timed CPU arm.  Nothing in the product (gnn-tf_b200/) links or calls it.
+ *
+ * PARITY UNPINNED: the reference's arithmetic lives in TensorFlow (un-vendored, un-pinned,
+ * not installable here), and the reference has no tests or golden vectors for this path; see
+ * oracle/gnntf_oracle.py for the assumptions.  This file is checked against that NumPy
+ * oracle (tests/test_oracle.py), which is itself pinned only by SURVEY.md's KAT-1/KAT-2.
+ *
+ * Threading mirrors TF-CPU: the SparseTensorDenseMatMul CPU functor is one sequential loop
+ * over the COO entries (kept single-threaded here); the element-wise ops around it run on
+ * Eigen's thread pool in TF (OpenMP here when compiled with -fopenmp).
+ *
+ * Reference lines followed (relative to the reference root):
+ *   gnntf/core/gnn/gnn.py:40-42                     column sums, D = divide_no_nan(1, sqrt(deg)), row then col scale
+ *   gnntf/core/gnn/architectures/filter.py:19       propagated = sparse_dense_matmul(G, features)
+ *   gnntf/core/gnn/architectures/filter.py:21       propagated*(1-a) + H0.value*a
+ *   gnntf/core/nn/layered.py:52-55                  the K-iteration driver loop
+ */
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+/* tf.sparse.reduce_sum(A, axis=0): one sum per COLUMN (gnn.py:41). */
+void oracle_colsum_f32(const int64_t* idx, const float* val, int64_t nnz, int64_t n, float* deg) {
+    memset(deg, 0, (size_t)n * sizeof(float));
+    for (int64_t i = 0; i < nnz; ++i) deg[idx[2 * i + 1]] += val[i];
+}
+
+/* gnn.py:41-42: D = divide_no_nan(1, sqrt(deg)); v_i = (v_i * D[row_i]) * D[col_i]. */
+void oracle_normalize_sym_f32(const int64_t* idx, const float* val, int64_t nnz, int64_t n,
+                              float* D, float* out) {
+    oracle_colsum_f32(idx, val, nnz, n, D);
+#pragma omp parallel for schedule(static)
+    for (int64_t j = 0; j < n; ++j) {
+        float s = sqrtf(D[j]);
+        D[j] = (s == 0.0f) ? 0.0f : 1.0f / s;
+    }
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < nnz; ++i) {
+        float r = val[i] * D[idx[2 * i]];
+        out[i] = r * D[idx[2 * i + 1]];
+    }
+}
+
+/* tf.sparse.sparse_dense_matmul on CPU (filter.py:19): out[row_i,:] += val_i * H[col_i,:] for the
+ * COO entries [lo, hi) in storage order; `out` must be zeroed by the caller for lo == 0. */
+void oracle_spmm_coo_f32(const int64_t* idx, const float* val, int64_t lo, int64_t hi,
+                         const float* H, int64_t F, float* out) {
+    for (int64_t i = lo; i < hi; ++i) {
+        const float v = val[i];
+        float* __restrict__ o = out + idx[2 * i] * F;
+        const float* __restrict__ h = H + idx[2 * i + 1] * F;
+        for (int64_t f = 0; f < F; ++f) o[f] += v * h[f];
+    }
+}
+
+/* filter.py:21: act = propagated*(1-a) + H0*a  (two multiplies, one add; no fused contraction). */
+void oracle_teleport_f32(const float* P, const float* H0, int64_t count, float a, float* out) {
+    const float one_minus_a = (float)(1 - (double)a), af = a;
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < count; ++i) {
+        volatile float x = P[i] * one_minus_a;
+        volatile float y = H0[i] * af;
+        out[i] = x + y;
+    }
+}
+
+/* K PPRIteration layers in eval mode (filter.py:17-22 under layered.py:52-55).  As in the
+ * reference, every iteration re-runs get_adjacency (filter.py:18) when renormalize != 0;
+ * with renormalize == 0 the normalised values are computed once (same result in eval mode).
+ * scratch: nnz floats (normalised values) + n floats (D) + n*F floats (propagated). */
+void oracle_appnp_propagate_f32(const int64_t* idx, const float* raw_val, int64_t nnz, int64_t n,
+                                const float* H0, int64_t F, float a, int K, int renormalize,
+                                float* scratch, float* H_out) {
+    float* norm = scratch;
+    float* D = norm + nnz;
+    float* P = D + n;
+    const float* H = H0;
+    for (int k = 0; k < K; ++k) {
+        if (k == 0 || renormalize) oracle_normalize_sym_f32(idx, raw_val, nnz, n, D, norm);
+        memset(P, 0, (size_t)n * F * sizeof(float));
+        oracle_spmm_coo_f32(idx, norm, 0, nnz, H, F, P);
+        oracle_teleport_f32(P, H0, n * F, a, H_out);
+        H = H_out;
+    }
+}

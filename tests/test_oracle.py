@@ -1,0 +1,167 @@
+"""CPU suite for the oracle itself: the NumPy restatement against the survey-derived known-answer
+tests (KAT-1 / KAT-2, SURVEY.md §8c — the reference ships no golden vectors), against the
+committed fixtures under tests/golden/, against independent scipy.sparse arithmetic, against its
+own fp64 twin, and the C restatement against the NumPy one."""
+import ctypes
+import json
+import os
+
+import numpy as np
+import pytest
+
+import gnntf_oracle as oracle
+
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def kat_graph():
+    import networkx as nx
+    G = nx.DiGraph()
+    for u in ["c", "a", "b", "d", "iso"]:
+        G.add_node(u)
+    G.add_edge("a", "b")
+    G.add_edge("b", "a")
+    G.add_edge("c", "d", weight=2.5)
+    G.add_edge("d", "d")
+    G.add_edge("a", "c")
+    return G
+
+
+def test_kat1_graph2adj_and_normalisation():
+    G = kat_graph()
+    assert oracle.graph2indices(G) == [[0, 3], [1, 2], [1, 0], [2, 1], [3, 3]]
+    idx, val, shape = oracle.graph2adj(G)
+    assert idx.tolist() == [[0, 3], [1, 2], [1, 0], [2, 1], [3, 3], [3, 0], [2, 1], [0, 1], [1, 2], [3, 3]]
+    assert val.tolist() == [2.5, 1, 1, 1, 1, 2.5, 1, 1, 1, 1] and shape == (5, 5)
+    assert oracle.column_sums(idx, val, 5).tolist() == [3.5, 3, 2, 4.5, 0]
+    _, nv, D = oracle.get_adjacency(idx, val, 5)
+    np.testing.assert_allclose(D, np.float32([0.5345225, 0.57735026, 0.70710677, 0.47140455, 0]), rtol=1e-7)
+    np.testing.assert_allclose(nv, np.float32([0.6299408, 0.40824828, 0.30860668, 0.40824828, 0.22222225] * 2), rtol=1e-7)
+
+
+def test_kat1_appnp_k10_fp64_and_fp32_drift():
+    idx, val, _ = oracle.graph2adj(kat_graph())
+    H0 = np.array([[(3 * i + j) / 7 - 1 for j in range(3)] for i in range(5)])
+    h64 = oracle.appnp_propagate(idx, val, 5, H0, 0.1, 10, dtype=np.float64)[-1]
+    expect = np.array([[-0.386717034, -0.242003374, -0.097289714], [-0.37323383, -0.233458343, -0.093682856],
+                       [-0.301202958, -0.181881658, -0.062560359], [-0.311411903, -0.151985331, 0.007441241],
+                       [0.071428571, 0.085714286, 0.1]])
+    np.testing.assert_allclose(h64, expect, atol=2e-9)
+    h32 = oracle.appnp_propagate(idx, val, 5, H0, 0.1, 10)[-1]
+    assert np.abs(h32 - h64).max() < 2e-6
+
+
+def test_kat2_masked_normalisation_is_not_symmetric():
+    idx, val, _ = oracle.graph2adj(kat_graph())
+    mv = oracle.sparse_dropout(val, 0.5, [1, 0, 1, 1, 0, 1, 1, 0, 1, 1])
+    assert mv.tolist() == [5, 0, 2, 2, 0, 5, 2, 0, 2, 2]
+    assert oracle.column_sums(idx, mv, 5).tolist() == [7, 4, 2, 7, 0]
+    _, nv, D = oracle.get_adjacency(idx, mv, 5)
+    np.testing.assert_allclose(D, np.float32([0.3779645, 0.5, 0.70710677, 0.3779645, 0]), rtol=1e-7)
+    np.testing.assert_allclose(nv, np.float32([0.7142858, 0, 0.3779645, 0.70710677, 0, 0.7142858, 0.70710677, 0,
+                                               0.70710677, 0.28571433]), rtol=2e-7)
+    dense = np.zeros((5, 5))
+    np.add.at(dense, (idx[:, 0], idx[:, 1]), nv)
+    assert dense[1, 0] > 0.37 and dense[0, 1] == 0 and abs(dense[2, 1] - 1.4142135) < 1e-6
+
+
+def test_golden_fixtures():
+    with open(os.path.join(GOLDEN, "kat.json")) as f:
+        kat = json.load(f)
+    for case in kat["cases"]:
+        idx = np.array(case["indices"], dtype=np.int64).reshape(-1, 2)
+        val = np.array(case["values"], dtype=np.float32)
+        n = case["n"]
+        if case.get("keep") is not None:
+            val = oracle.sparse_dropout(val, case["rate"], case["keep"])
+        _, nv, _ = oracle.get_adjacency(idx, val, n, case["normalized"], case["add_eye"])
+        np.testing.assert_allclose(nv, np.array(case["norm_values"], np.float32), rtol=3e-7, err_msg=case["name"])
+        H0 = np.array(case["H0"], np.float32)
+        out = oracle.appnp_propagate(idx, val, n, H0, case["alpha"], case["K"])[-1] if case["normalized"] == "symmetric" and case["add_eye"] == "none" else None
+        if out is not None:
+            oracle.assert_close(out, np.array(case["H_K"]), what=case["name"])
+
+
+def test_sparse_ops_against_scipy():
+    import scipy.sparse as sp
+    rng = np.random.default_rng(0)
+    n, e, F = 400, 5000, 17
+    edges = rng.integers(0, n, (e, 2))
+    w = rng.random(e).astype(np.float32) + 0.5
+    idx, val, _ = oracle.graph2adj_arrays(edges, w, n)
+    A = sp.coo_matrix((val.astype(np.float64), (idx[:, 0], idx[:, 1])), shape=(n, n)).tocsr()  # coalesces duplicates
+    deg = np.asarray(A.sum(axis=0)).ravel()
+    np.testing.assert_allclose(oracle.column_sums(idx, val, n, np.float64), deg, rtol=1e-12)
+    d = np.where(deg > 0, 1 / np.sqrt(np.where(deg > 0, deg, 1)), 0)
+    Ahat = sp.diags(d) @ A @ sp.diags(d)
+    _, nv, _ = oracle.get_adjacency(idx, val, n, dtype=np.float64)
+    H = rng.standard_normal((n, F))
+    np.testing.assert_allclose(oracle.spmm_coo(idx, nv, H, dtype=np.float64), Ahat @ H, rtol=1e-10, atol=1e-12)
+    np.testing.assert_allclose(oracle.spmm_coo_T(idx, nv, H, n, dtype=np.float64), Ahat.T @ H, rtol=1e-10, atol=1e-12)
+    oracle.assert_close(oracle.spmm_coo(idx, nv.astype(np.float32), H.astype(np.float32)), Ahat @ H)
+    # K-step loop == the closed-form polynomial
+    a, K = 0.1, 6
+    expect, P = np.zeros_like(H), H.copy()
+    for j in range(K):
+        expect += a * (1 - a) ** j * P
+        P = Ahat @ P
+    expect += (1 - a) ** K * P
+    got = oracle.appnp_propagate(idx, val, n, H, a, K, dtype=np.float64)[-1]
+    np.testing.assert_allclose(got, expect, rtol=1e-10, atol=1e-12)
+
+
+def test_backward_is_the_adjoint():
+    """<appnp(H0), G> == <H0, appnp_bwd(G)> with per-iteration masked (non-symmetric) adjacencies."""
+    rng = np.random.default_rng(1)
+    n, e, F, K, a = 120, 900, 5, 4, 0.15
+    idx, val, _ = oracle.graph2adj_arrays(rng.integers(0, n, (e, 2)), None, n)
+    keeps = [rng.random(idx.shape[0]) >= 0.5 for _ in range(K)]
+    H0, G = rng.standard_normal((n, F)), rng.standard_normal((n, F))
+    out = oracle.appnp_propagate(idx, val, n, H0, a, K, 0.5, keeps, training=True, dtype=np.float64)[-1]
+    nvs = [oracle.get_adjacency(idx, oracle.sparse_dropout(val, 0.5, k), n, dtype=np.float64)[1] for k in keeps]
+    dH0 = oracle.appnp_propagate_bwd(idx, nvs, G, a, dtype=np.float64)
+    assert abs((out * G).sum() - (H0 * dH0).sum()) < 1e-9 * abs((out * G).sum())
+
+
+def test_csr_view_is_a_stable_row_sort():
+    rng = np.random.default_rng(2)
+    n, e = 60, 500
+    idx, val, _ = oracle.graph2adj_arrays(rng.integers(0, n, (e, 2)), None, n)
+    row_ptr, col, pos, perm_T = oracle.csr_from_coo(idx, n)
+    assert row_ptr[0] == 0 and row_ptr[-1] == 2 * e and np.all(np.diff(row_ptr) >= 0)
+    rows = np.repeat(np.arange(n), np.diff(row_ptr))
+    assert np.array_equal(idx[pos, 0], rows) and np.array_equal(idx[pos, 1], col)
+    for r in range(n):
+        seg = pos[row_ptr[r]:row_ptr[r + 1]]
+        assert np.all(np.diff(seg) > 0)  # COO order kept inside each row
+    assert np.array_equal(rows[perm_T], col) and np.array_equal(col[perm_T], rows)
+
+
+def test_add_eye_and_modes():
+    idx, val, _ = oracle.graph2adj(kat_graph())
+    i2, v2, _ = oracle.get_adjacency(idx, val, 5, "symmetric", "before")
+    assert i2.shape[0] == 15 and oracle.column_sums(i2[:10], val, 5).tolist() == [3.5, 3, 2, 4.5, 0]
+    assert v2[14] == 1.0  # isolated node: deg 1 -> D = 1 -> value 1
+    i3, v3, _ = oracle.get_adjacency(idx, val, 5, "bipartite", "after")
+    assert v3[10:].tolist() == [1] * 5 and abs(v3[0] - 2.5 / 3.5) < 1e-7
+    with pytest.raises(Exception, match="Invalid matrix normalization"):
+        oracle.get_adjacency(idx, val, 5, "laplacian")
+
+
+def test_c_oracle_matches_numpy_oracle(oracle_c):
+    rng = np.random.default_rng(3)
+    n, e, F, K = 3000, 40000, 47, 10
+    idx, val, _ = oracle.graph2adj_arrays(rng.integers(0, n, (e, 2)), rng.random(e).astype(np.float32) + 0.5, n)
+    H0 = rng.standard_normal((n, F)).astype(np.float32)
+    nnz = idx.shape[0]
+    out = np.empty_like(H0)
+    scratch = np.empty(nnz + n + n * F, np.float32)
+    P = ctypes.c_void_p
+    oracle_c.oracle_appnp_propagate_f32.argtypes = [P, P, ctypes.c_int64, ctypes.c_int64, P, ctypes.c_int64,
+                                                    ctypes.c_float, ctypes.c_int, ctypes.c_int, P, P]
+    oracle_c.oracle_appnp_propagate_f32(idx.ctypes.data, val.ctypes.data, nnz, n, H0.ctypes.data, F,
+                                        ctypes.c_float(0.1), K, 1, scratch.ctypes.data, out.ctypes.data)
+    expect = oracle.appnp_propagate(idx, val, n, H0, 0.1, K)[-1]
+    oracle.assert_close(out, expect, rtol=1e-6, what="C oracle vs NumPy oracle")
+    _, nv, D = oracle.get_adjacency(idx, val, n)
+    np.testing.assert_allclose(scratch[:nnz], nv, rtol=2e-7)
