@@ -1,0 +1,372 @@
+#!/usr/bin/env python
+"""Benchmark of the hot path: APPNP K=10 propagation (BASELINE.json `metric`).
+
+  python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+  python bench.py --impl reference --gpus N --steps K ...   # the reference's CPU path (oracle port)
+
+One "step" = one full K=10 propagation  H <- (1-a)·Â·H + a·H0  (ten fused launches) over the
+named synthetic workload with Â built and normalised beforehand and H0 resident in HBM.
+`value` = edge·features processed per second = nnz·F·K_iter·steps / time (whole job, all GPUs);
+`ms_per_step` = the metric's other half, the absolute K=10 propagation time.  Prints ONE JSON line
+on stdout (rank 0); everything else goes to stderr.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (os.path.join(ROOT, "gnn-tf_b200"), ROOT):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+import synthetic  # noqa: E402
+
+METRIC = "appnp_k10_propagation_edge_features_per_s"
+UNIT = "edge_features/s"
+K_ITER = 10
+ALPHA = 0.1
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, copy burst)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def step_bytes(n, nnz, F):
+    """Algorithmic bytes of one fused APPNP step: int32 col + fp32 val per entry,
+    int32 row_ptr, read H_k, read H0, write H_{k+1}; every array touched once."""
+    return 8 * nnz + 4 * (n + 1) + 12 * n * F
+
+
+# ----------------------------------------------------------------------------------------------
+# clocks sampling (B200_PROFILING.md recipe)
+# ----------------------------------------------------------------------------------------------
+class ClockSampler:
+    FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+              "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index=0):
+        self.proc, self.path, self.gpu = None, None, gpu_index
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.gpu)],
+                                         stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception as e:  # nvidia-smi missing
+            log("clock sampler unavailable:", e)
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in open(self.path):
+            parts = [x.strip() for x in line.split(",")]
+            if len(parts) < 9:
+                continue
+            try:
+                sm.append(float(parts[1]))
+                mx.append(float(parts[2]))
+            except ValueError:
+                continue
+            for name, flag in zip(names, parts[5:9]):
+                if flag.lower().startswith("active"):
+                    reasons.add(name)
+        os.unlink(self.path)
+        if sm:
+            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+# ----------------------------------------------------------------------------------------------
+# workload
+# ----------------------------------------------------------------------------------------------
+def make_workload(args, device):
+    n, e, f_default, classes = synthetic.SHAPES[args.workload]
+    F = args.features or (classes if args.workload == "cora" else f_default)
+    t0 = time.time()
+    if args.workload in synthetic.POWERLAW:
+        n, edges = synthetic.shaped_edges(args.workload, seed=0, ordering=args.ordering, device=device, scale=args.scale)
+    else:
+        G = synthetic.citation_graph(n, e, seed=0)
+        import gnntf
+        edges = torch.as_tensor(np.asarray(gnntf.graph2indices(G), dtype=np.int64)).to(device)
+    log(f"[workload] {args.workload}: n={n} E={edges.shape[0]} F={F} ordering={args.ordering} generated in {time.time() - t0:.1f}s")
+    return n, edges, F
+
+
+def config_dict(args, n, E, nnz, F):
+    return {"workload": f"APPNP K={K_ITER} a={ALPHA} on {args.workload}-shaped synthetic graph", "nodes": n, "edges": E,
+            "nnz": nnz, "features": F, "iterations": K_ITER, "alpha": ALPHA, "ordering": args.ordering,
+            "scale": args.scale, "normalisation": "symmetric, eval mode (prebuilt)",
+            "l2": "no explicit flush: per-step working set (CSR + 3 feature matrices) exceeds the 126 MB L2"
+                  if step_bytes(n, nnz, F) > 3 * 126e6 else "working set fits L2: flushed by a 256 MB write between steps"}
+
+
+# ----------------------------------------------------------------------------------------------
+# CPU arm (oracle port of the reference's TF-CPU path)
+# ----------------------------------------------------------------------------------------------
+def load_oracle_c():
+    import __graft_entry__ as entry
+    lib = ctypes.CDLL(entry.build_oracle())
+    P = ctypes.c_void_p
+    lib.oracle_normalize_sym_f32.argtypes = [P, P, ctypes.c_int64, ctypes.c_int64, P, P]
+    lib.oracle_spmm_coo_f32.argtypes = [P, P, ctypes.c_int64, ctypes.c_int64, P, ctypes.c_int64, P]
+    lib.oracle_teleport_f32.argtypes = [P, P, ctypes.c_int64, ctypes.c_float, P]
+    return lib
+
+
+def cpu_arm(n, edges_cpu, F, seconds_per_step, steps, warmup):
+    """Times the oracle's restatement of filter.py:19-21 (COO-order SpMM loop as in TF-CPU's
+    SparseTensorDenseMatMul functor + teleport) on a bounded prefix of the COO list."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import gnntf_oracle as oracle
+    lib = load_oracle_c()
+    idx, val, _ = oracle.graph2adj_arrays(edges_cpu, None, n)
+    nnz = idx.shape[0]
+    D = np.empty(n, np.float32)
+    norm = np.empty(nnz, np.float32)
+    lib.oracle_normalize_sym_f32(idx.ctypes.data, val.ctypes.data, nnz, n, D.ctypes.data, norm.ctypes.data)
+    H = np.random.default_rng(1).standard_normal((n, F)).astype(np.float32)
+    P = np.zeros((n, F), np.float32)
+    out = np.empty((n, F), np.float32)
+    # calibrate on 2M entries, then size the sample for ~seconds_per_step
+    cal = min(nnz, 2_000_000)
+    t0 = time.perf_counter()
+    lib.oracle_spmm_coo_f32(idx.ctypes.data, norm.ctypes.data, 0, cal, H.ctypes.data, F, P.ctypes.data)
+    rate = cal * F / max(time.perf_counter() - t0, 1e-9)
+    sample = int(min(nnz, max(cal, rate * seconds_per_step / F)))
+    times = []
+    for it in range(warmup + steps):
+        P[:] = 0
+        t0 = time.perf_counter()
+        lib.oracle_spmm_coo_f32(idx.ctypes.data, norm.ctypes.data, 0, sample, H.ctypes.data, F, P.ctypes.data)
+        frac = sample / nnz
+        rows = max(1, int(n * frac))  # the teleport pass scaled to the same fraction of the step
+        lib.oracle_teleport_f32(P.ctypes.data, H.ctypes.data, rows * F, ctypes.c_float(ALPHA), out.ctypes.data)
+        dt = time.perf_counter() - t0
+        if it >= warmup:
+            times.append(dt)
+    t = float(np.mean(times))
+    value = sample * F / t
+    omp = int(os.environ.get("OMP_NUM_THREADS", os.cpu_count() or 1))
+    desc = (f"{sample} of {nnz} COO entries (prefix, storage order) x F={F}: one PPR iteration's SpMM + teleport, "
+            f"{len(times)} timed reps; SpMM loop single-threaded as in TF-CPU, element-wise pass on {omp} OpenMP threads")
+    return value, t, sample, desc, omp
+
+
+# ----------------------------------------------------------------------------------------------
+# GPU arm
+# ----------------------------------------------------------------------------------------------
+def dist_setup(n_gpus):
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", 0))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    if world > 1:
+        torch.cuda.set_device(local)
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    else:
+        torch.cuda.set_device(0)
+    return rank, local, world
+
+
+def gpu_arm(args):
+    import gnntf
+    from gnntf import ops
+    rank, local, world = dist_setup(args.gpus)
+    dev = torch.device("cuda", local)
+    hbm_peak, peak_src = peaks()
+    n, edges, F = make_workload(args, dev)
+    E = edges.shape[0]
+
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    adj = gnntf.edges2adj(edges, None, n)
+    A = adj.normalized("symmetric")
+    torch.cuda.synchronize()
+    build_s = time.perf_counter() - t0
+    nnz = adj.csr.nnz
+    log(f"[build] graph2adj + CSR + normalise: {build_s * 1e3:.1f} ms (nnz={nnz}, long rows={adj.csr.n_long}, pieces={adj.csr.n_chunks})")
+    H0 = synthetic.features(n, F, seed=1, device=dev)
+
+    if world > 1:
+        from gnntf import dist as gdist
+        prop = gdist.ShardedPropagator(adj, A, F, rank, world)
+        H0_local = H0[prop.lo:prop.hi].contiguous()
+        run = lambda: prop.propagate(H0_local, ALPHA, K_ITER)  # noqa: E731
+        launches_per_step = prop.launches_per_propagation(K_ITER)
+        del H0
+    else:
+        out = torch.empty_like(H0)
+        scratch = torch.empty_like(H0)
+        run = lambda: ops.propagate_raw(A, H0, ALPHA, K_ITER, out=out, scratch=scratch)  # noqa: E731
+        launches_per_step = K_ITER * (3 if adj.csr.n_long > 0 else 1)
+    flush = None
+    if step_bytes(n, nnz, F) <= 3 * 126e6:
+        flush = torch.empty(64 * 1024 * 1024, dtype=torch.float32, device=dev)
+
+    def barrier():
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        run()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    barrier()
+    for s, e_ in evs:
+        if flush is not None:
+            flush.fill_(1.0)
+        s.record()
+        run()
+        e_.record()
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    per_step_ms = torch.tensor([s.elapsed_time(e_) for s, e_ in evs], dtype=torch.float64, device=dev)
+    total_ms = per_step_ms.sum().reshape(1)
+    if world > 1:
+        torch.distributed.all_reduce(total_ms, op=torch.distributed.ReduceOp.MAX)
+    total_ms = float(total_ms.item())
+    ms_per_step = total_ms / args.steps
+    value = nnz * F * K_ITER * args.steps / (total_ms * 1e-3)
+
+    result = None
+    if rank == 0:
+        bstep = step_bytes(n, nnz, F)
+        achieved = bstep * K_ITER / (ms_per_step * 1e-3) / 1e9
+        result = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "config": config_dict(args, n, E, nnz, F),
+            "propagation_ms": {"mean": ms_per_step, "min": float(per_step_ms.min().item()),
+                               "median": float(per_step_ms.median().item())},
+            "clocks": clocks, "gpu_launches": launches_per_step * args.steps,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
+                         "traffic": None, "peak_source": peak_src, "frac_of_nominal_8TBs": achieved / 8000.0,
+                         "kernel": "fused APPNP step (spmm_rows_kernel + long-row pieces/reduce)",
+                         "algorithmic_bytes_per_launch": bstep,
+                         "avg_launch_ms": ms_per_step / K_ITER,
+                         "note": "achieved = B_step / (timed region / (steps*K)); B_step = 8*nnz + 4*(N+1) + 12*N*F"},
+            "csr_build_ms": build_s * 1e3,
+        }
+        if world > 1:
+            result["roofline"]["note"] += f"; aggregate over {world} GPUs, peak is per-GPU x {world}"
+            result["roofline"]["peak"] = hbm_peak * world
+            result["roofline"]["frac"] = achieved / (hbm_peak * world)
+
+    # ---- e2e: host buffers in, host buffers out, through the public API ------------------------
+    if world == 1:
+        H0_host = H0.cpu().pin_memory()
+        out_host = torch.empty_like(H0_host).pin_memory()
+        bufs = [H0, out, scratch]
+        reps = max(1, min(args.steps, 5))
+        ops.appnp_propagate_host(A, H0_host, ALPHA, K_ITER, out_host=out_host, bufs=bufs)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            ops.appnp_propagate_host(A, H0_host, ALPHA, K_ITER, out_host=out_host, bufs=bufs)
+        torch.cuda.synchronize()
+        e2e_s = (time.perf_counter() - t0) / reps
+        result["e2e"] = {"value": nnz * F * K_ITER / e2e_s, "unit": UNIT, "h2d_bytes_per_step": n * F * 4,
+                         "d2h_bytes_per_step": n * F * 4, "ms_per_step": e2e_s * 1e3,
+                         "api": "gnntf.appnp_propagate_host -> gnntf_appnp_propagate_host_f32 (pinned host H0 in, host H_K out)"}
+    else:
+        e2e = prop.propagate_host_timed(ALPHA, K_ITER, reps=max(1, min(args.steps, 3)))
+        if rank == 0:
+            result["e2e"] = {"value": nnz * F * K_ITER / e2e["seconds"], "unit": UNIT,
+                             "h2d_bytes_per_step": e2e["h2d"], "d2h_bytes_per_step": e2e["d2h"],
+                             "ms_per_step": e2e["seconds"] * 1e3, "api": "gnntf.dist.ShardedPropagator.propagate_host"}
+
+    # ---- CPU baseline (rank 0, N=1 only) ----------------------------------------------------
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        t0 = time.time()
+        v, t, sample, desc, omp = cpu_arm(n, edges.cpu().numpy(), F, seconds_per_step=6.0, steps=2, warmup=1)
+        result["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": omp, "kind": "port", "sample": desc,
+                                  "host_cpus": os.cpu_count(), "wall_s": time.time() - t0}
+    if rank == 0:
+        os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+        print(json.dumps(result), flush=True)
+    if world > 1:
+        torch.distributed.barrier()
+        torch.distributed.destroy_process_group()
+
+
+def reference_arm(args):
+    rank = int(os.environ.get("RANK", 0))
+    if rank != 0:
+        return
+    n, edges, F = make_workload(args, "cpu")
+    nnz = 2 * edges.shape[0]
+    budget = 150.0 / max(1, args.steps + args.warmup)
+    v, t, sample, desc, omp = cpu_arm(n, edges.numpy(), F, seconds_per_step=min(20.0, budget), steps=args.steps,
+                                      warmup=args.warmup)
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": K_ITER * nnz * F / v * 1e3, "ms_per_step_note": "K=10 propagation time extrapolated from the sampled rate",
+            "sample_ms": t * 1e3, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": config_dict(args, n, edges.shape[0], nnz, F),
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": omp, "kind": "port", "sample": desc,
+                             "host_cpus": os.cpu_count()},
+            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "note": "the reference (TensorFlow) cannot be installed in this image; this is the oracle's C port of its "
+                    "CPU path (COO-order single-threaded SpMM loop + teleport), timed on a bounded sample"}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--workload", default="products", choices=sorted(synthetic.SHAPES))
+    ap.add_argument("--ordering", default="local", choices=["local", "random"])
+    ap.add_argument("--features", type=int, default=0, help="feature width (default: the shape's)")
+    ap.add_argument("--scale", type=float, default=1.0, help="shrink the graph (tests only; 1.0 = BASELINE size)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        reference_arm(args)
+    else:
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback (use --impl reference for the CPU arm)")
+        gpu_arm(args)
+
+
+if __name__ == "__main__":
+    main()

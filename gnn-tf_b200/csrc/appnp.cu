@@ -141,12 +141,20 @@ extern "C" int gnntf_appnp_propagate_host_f32(const gnntf_csr_t* A, const float*
     if (n == 0 || F == 0) return GNNTF_OK;
     if (H0_host == nullptr || out_host == nullptr || dev_H0 == nullptr || dev_out == nullptr)
         return GNNTF_E_NULL;
-    GNNTF_CUDA_TRY(cudaMemcpy2DAsync(dev_H0, ld * sizeof(float), H0_host, F * sizeof(float),
-                                     F * sizeof(float), n, cudaMemcpyHostToDevice, st));
+    if (ld == F) {  // dense on both sides: one linear DMA (2-D copies are issued row by row)
+        GNNTF_CUDA_TRY(cudaMemcpyAsync(dev_H0, H0_host, (size_t)n * F * sizeof(float), cudaMemcpyHostToDevice, st));
+    } else {
+        GNNTF_CUDA_TRY(cudaMemcpy2DAsync(dev_H0, ld * sizeof(float), H0_host, F * sizeof(float),
+                                         F * sizeof(float), n, cudaMemcpyHostToDevice, st));
+    }
     int rc = propagate_impl(A, 1, K, dev_H0, dev_out, dev_scratch, ld, F, alpha, st);
     if (rc != GNNTF_OK) return rc;
-    GNNTF_CUDA_TRY(cudaMemcpy2DAsync(out_host, F * sizeof(float), dev_out, ld * sizeof(float),
-                                     F * sizeof(float), n, cudaMemcpyDeviceToHost, st));
+    if (ld == F) {
+        GNNTF_CUDA_TRY(cudaMemcpyAsync(out_host, dev_out, (size_t)n * F * sizeof(float), cudaMemcpyDeviceToHost, st));
+    } else {
+        GNNTF_CUDA_TRY(cudaMemcpy2DAsync(out_host, F * sizeof(float), dev_out, ld * sizeof(float),
+                                         F * sizeof(float), n, cudaMemcpyDeviceToHost, st));
+    }
     return GNNTF_OK;
 }
 

@@ -1,6 +1,6 @@
 // Helpers for the row-sharded multi-GPU path (contiguous node-range split, one process per GPU).
-// The halo exchange itself is an NCCL all-to-all issued by the host shim; these kernels prepare
-// the shard-local CSR and pack the rows each peer needs.  The propagation step of the reference
+// The halo exchange itself is an NCCL all-to-all issued by the host shim; this kernel packs the
+// rows each peer needs into the send buffer.  The propagation step of the reference
 // (gnntf/core/gnn/architectures/filter.py:19-22) is otherwise unchanged: the local CSR simply
 // addresses [owned rows | halo rows].
 #include <algorithm>
@@ -8,25 +8,6 @@
 #include "common.cuh"
 
 namespace gnntf {
-
-__global__ void localize_kernel(int32_t* __restrict__ col_idx, int64_t nnz, int32_t lo, int32_t hi,
-                                const int32_t* __restrict__ halo_cols, int32_t n_halo) {
-    const int32_t n_local = hi - lo;
-    for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < nnz;
-         p += (int64_t)gridDim.x * blockDim.x) {
-        const int32_t c = col_idx[p];
-        if (c >= lo && c < hi) {
-            col_idx[p] = c - lo;
-        } else {
-            int32_t a = 0, b = n_halo;  // lower_bound
-            while (a < b) {
-                const int32_t m = (a + b) >> 1;
-                if (__ldg(halo_cols + m) < c) a = m + 1; else b = m;
-            }
-            col_idx[p] = n_local + a;
-        }
-    }
-}
 
 // out[i, 0:F] = H[send_idx[i], 0:F]; one warp per row, float4 when the layout allows.
 template <int VEC>
@@ -45,19 +26,6 @@ __global__ void halo_pack_kernel(const float* __restrict__ H, int64_t ld, const 
 }  // namespace gnntf
 
 using namespace gnntf;
-
-extern "C" int gnntf_csr_localize(int32_t* col_idx, int64_t nnz, int64_t lo, int64_t hi,
-                                  const int32_t* halo_cols, int64_t n_halo, void* stream) {
-    if (nnz < 0 || lo < 0 || hi < lo || hi > 0x7ffffffeLL || n_halo < 0 || n_halo > 0x7ffffffeLL)
-        return GNNTF_E_SIZE;
-    if (nnz == 0) return GNNTF_OK;
-    if (col_idx == nullptr || (n_halo > 0 && halo_cols == nullptr)) return GNNTF_E_NULL;
-    const int grid = (int)std::min<int64_t>(ceil_div(nnz, 256), (int64_t)kNumSMs * 16);
-    localize_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(col_idx, nnz, (int32_t)lo, (int32_t)hi,
-                                                            halo_cols, (int32_t)n_halo);
-    GNNTF_LAUNCH_CHECK();
-    return GNNTF_OK;
-}
 
 extern "C" int gnntf_halo_pack_f32(const float* H, int64_t ld, const int32_t* send_idx, int64_t n_send,
                                    float* out, int64_t ldo, int64_t F, void* stream) {

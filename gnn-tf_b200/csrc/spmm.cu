@@ -17,6 +17,8 @@
 // here and run as fixed-size pieces on separate warps (spmm_chunk_kernel), whose partial sums are
 // combined in piece order by spmm_long_reduce_kernel: deterministic, no float atomics.
 #include <algorithm>
+#include <cstdlib>
+#include <type_traits>
 
 #include "spmm.cuh"
 
@@ -145,6 +147,273 @@ spmm_rows_kernel(const int* __restrict__ row_ptr, const int* __restrict__ col_id
 #pragma unroll
         for (int s = 0; s < NSLOT; ++s)
             if (fok[s]) apply_epilogue<VEC>(epi, out_row, fo[s], acc[s]);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Bulk-copy kernel (wide rows: F >= 68 floats, 16-byte aligned rows).
+//
+// Why it exists (profiles/r1/01): on the products shape the per-row register
+// kernel is latency-bound — DRAM, L1 and the issue slots are each ~50 % busy — because the bytes a
+// warp can keep in flight are capped by registers and by the 6 counting scoreboards (a rolling
+// register ring was measured 2x SLOWER: waiting for the oldest load also waits for the youngest;
+// a shared-memory ring fed by 16-byte cp.async was 2.5x slower: LDGSTS.128 sustains ~16 B/clk/SM).
+// Here every gathered feature row travels global -> shared as ONE bulk async copy (PTX
+// cp.async.bulk, SASS UBLKCP: the TMA engine, no registers, no L1, no scoreboard) that signals an
+// mbarrier with its byte count.  Each warp owns a private ring of S stages x G row images and S
+// mbarriers; it keeps up to S*G gathers in flight across row boundaries, so bytes in flight are
+// bounded by shared memory (~200 KB/SM), not by the register file.
+//
+// A warp owns R consecutive rows at a time and walks such chunks with a grid stride: the grid
+// sweeps the matrix as one wavefront, which keeps the band of gathered rows that L2 must hold
+// narrow.  Rows above the split threshold are left to the piece kernels, as in spmm_rows_kernel.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_addr(const void* p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+// A byte-count mismatch would spin forever and wedge the GPU: trap after ~2 s instead.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    if (mbar_try_wait(bar, parity)) return;
+    const long long t0 = clock64();
+    while (!mbar_try_wait(bar, parity)) {
+        if (clock64() - t0 > 4000000000LL) __trap();
+    }
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                 "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ uint64_t policy_evict_first() {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ int ld_once(const int* p, uint64_t pol) {
+    int v;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.s32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(pol));
+    return v;
+}
+__device__ __forceinline__ float ld_once(const float* p, uint64_t pol) {
+    float v;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.f32 %0, [%1], %2;" : "=f"(v) : "l"(p), "l"(pol));
+    return v;
+}
+__device__ __forceinline__ float4 ld_once4(const float* p, uint64_t pol) {
+    float4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.f32 {%0,%1,%2,%3}, [%4], %5;"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+                 : "l"(p), "l"(pol));
+    return v;
+}
+__device__ __forceinline__ void st_once4(float* p, float4 v, uint64_t pol) {
+    asm volatile("st.global.L1::no_allocate.L2::cache_hint.v4.f32 [%0], {%1,%2,%3,%4}, %5;" ::"l"(p),
+                 "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "l"(pol)
+                 : "memory");
+}
+
+// Epilogue with the teleport row already in registers and evict-first stores; the rarely used
+// dropout-mask / backward-accumulate variants go through the generic path.
+__device__ __forceinline__ void epilogue_fast(const Epilogue& e, int64_t row, int f, const float4& a,
+                                              const float4& h0, uint64_t pol) {
+    if (e.keep != nullptr || e.ACC != nullptr) {
+        apply_epilogue<4>(e, row, f, Vec<4>{{a.x, a.y, a.z, a.w}});
+        return;
+    }
+    float4 o = make_float4(a.x * e.s, a.y * e.s, a.z * e.s, a.w * e.s);
+    if (e.H0 != nullptr) {
+        o.x = __fadd_rn(o.x, __fmul_rn(h0.x, e.t));
+        o.y = __fadd_rn(o.y, __fmul_rn(h0.y, e.t));
+        o.z = __fadd_rn(o.z, __fmul_rn(h0.z, e.t));
+        o.w = __fadd_rn(o.w, __fmul_rn(h0.w, e.t));
+    }
+    if (e.act == GNNTF_ACT_RELU) {
+        o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f);
+    }
+    if (e.C != nullptr) st_once4(e.C + row * e.ldc + f, o, pol);
+}
+
+// G row images per stage, S stages per warp.  Entry e of a stream lives in stage (e/G)%S, slot e%G.
+template <int NSLOT, int G, int S, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32)
+spmm_bulk_kernel(const int* __restrict__ row_ptr, const int* __restrict__ col_idx,
+                 const float* __restrict__ val, const int* __restrict__ row_map,
+                 const float* __restrict__ B, int64_t ldb, int n_rows, int long_threshold,
+                 int rows_per_chunk, int tile_floats, Epilogue epi) {
+    static_assert(32 % G == 0 && G <= 32, "G must divide 32");
+    extern __shared__ __align__(128) unsigned char bulk_smem[];
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const int F = epi.F;
+    const int f_base = blockIdx.y * tile_floats;
+    const int width = min(tile_floats, F - f_base);        // floats of this feature tile
+    const uint32_t row_bytes = (uint32_t)width * 4u;       // multiple of 16 (F % 4 == 0)
+    const uint32_t slot_bytes = (uint32_t)tile_floats * 4u;
+    const uint64_t pol = policy_evict_first();
+
+    unsigned char* my_ring = bulk_smem + (size_t)warp * (S * G) * slot_bytes;
+    const uint32_t ring_u32 = smem_addr(my_ring);
+    const uint32_t bars_u32 = smem_addr(bulk_smem + (size_t)WARPS * (S * G) * slot_bytes) + warp * S * 8;
+    if (lane < S) mbar_init(bars_u32 + lane * 8, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    __syncwarp();
+
+    int fo[NSLOT];
+    bool fok[NSLOT];
+#pragma unroll
+    for (int s = 0; s < NSLOT; ++s) {
+        const int in_tile = (s * 32 + lane) * 4;
+        fo[s] = f_base + in_tile;
+        fok[s] = in_tile < width;
+    }
+    const float* Bt = B + f_base;
+    uint32_t phase_bits = 0;  // bit s = parity to wait for on stage s next
+
+    const int n_chunks = (n_rows + rows_per_chunk - 1) / rows_per_chunk;
+    const int warp_stride = gridDim.x * WARPS;
+    float4 acc[NSLOT], h0[NSLOT];
+#pragma unroll
+    for (int s = 0; s < NSLOT; ++s) h0[s] = make_float4(0.f, 0.f, 0.f, 0.f);
+
+    for (int chunk = blockIdx.x * WARPS + warp; chunk < n_chunks; chunk += warp_stride) {
+        const int r0 = chunk * rows_per_chunk;
+        const int nr = min(rows_per_chunk, n_rows - r0);
+        const int rp = (lane <= nr) ? __ldg(row_ptr + r0 + lane) : 0;  // lane i holds row_ptr[r0+i]
+        const int rp_next = __shfl_down_sync(0xffffffffu, rp, 1);
+        const bool is_long = (lane < nr) && long_threshold > 0 && (rp_next - rp) > long_threshold;
+        const unsigned long_mask = __ballot_sync(0xffffffffu, is_long);
+        int cur_row = 0, cur_end = 0;
+
+        auto prefetch_h0 = [&](int local_row) {
+            if (epi.H0 != nullptr) {
+                const int64_t m = row_map ? (int64_t)__ldg(row_map + r0 + local_row) : (int64_t)(r0 + local_row);
+#pragma unroll
+                for (int s = 0; s < NSLOT; ++s)
+                    if (fok[s]) h0[s] = ld_once4(epi.H0 + m * epi.ldh + fo[s], pol);
+            }
+        };
+        auto flush_row = [&](int seg_end) {  // write the current row, advance, prefetch the next teleport row
+            const int64_t m = row_map ? (int64_t)__ldg(row_map + r0 + cur_row) : (int64_t)(r0 + cur_row);
+#pragma unroll
+            for (int s = 0; s < NSLOT; ++s) {
+                if (fok[s]) epilogue_fast(epi, m, fo[s], acc[s], h0[s], pol);
+                acc[s] = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            ++cur_row;
+            cur_end = __shfl_sync(0xffffffffu, rp, min(cur_row + 1, 31));
+            if (cur_row < seg_end) prefetch_h0(cur_row);
+        };
+
+        int a = 0;
+        while (a < nr) {  // maximal runs [a,b) of rows that are not split
+            if ((long_mask >> a) & 1u) { ++a; continue; }
+            int b = nr;
+            const unsigned rest = long_mask >> a;
+            if (rest) b = a + __ffs(rest) - 1;
+            const int P0 = __shfl_sync(0xffffffffu, rp, a);
+            const int P1 = __shfl_sync(0xffffffffu, rp, b);
+            cur_row = a;
+            cur_end = __shfl_sync(0xffffffffu, rp, a + 1);
+#pragma unroll
+            for (int s = 0; s < NSLOT; ++s) acc[s] = make_float4(0.f, 0.f, 0.f, 0.f);
+            prefetch_h0(a);
+            while (cur_row < b && cur_end == P0) flush_row(b);  // leading empty rows
+            if (P0 == P1) { a = b; continue; }
+
+            const int n_ent = P1 - P0;
+            const int n_groups = (n_ent + G - 1) / G;
+            // (col,val) batches of 32 entries; *_nx prefetched one batch ahead of their first use
+            int cb = 0, cb_nx = 0;     // issue side
+            float vb = 0.f, vb_nx = 0.f;  // consume side
+            if (lane < n_ent) { cb = ld_once(col_idx + P0 + lane, pol); vb = ld_once(val + P0 + lane, pol); }
+            if (32 + lane < n_ent) { cb_nx = ld_once(col_idx + P0 + 32 + lane, pol); vb_nx = ld_once(val + P0 + 32 + lane, pol); }
+            int cb_base = 0;  // stream index of cb's lane 0
+
+            auto issue_group = [&](int g) {  // copies of group g into stage g % S
+                const int e0 = g * G;
+                if (e0 >= cb_base + 32) {  // the issue side moves into the next batch
+                    cb = cb_nx;
+                    cb_base += 32;
+                    cb_nx = (cb_base + 32 + lane < n_ent) ? ld_once(col_idx + P0 + cb_base + 32 + lane, pol) : 0;
+                }
+                const int cnt = min(G, n_ent - e0);
+                const int stage = g % S;
+                const uint32_t bar = bars_u32 + stage * 8;
+                if (lane == 0) mbar_expect_tx(bar, (uint32_t)cnt * row_bytes);
+                __syncwarp();
+                const int c = __shfl_sync(0xffffffffu, cb, (e0 - cb_base + lane) & 31);
+                if (lane < cnt)
+                    bulk_g2s(ring_u32 + (uint32_t)(stage * G + lane) * slot_bytes, Bt + (int64_t)c * ldb, row_bytes, bar);
+            };
+
+            const int pre = min(S, n_groups);
+            for (int g = 0; g < pre; ++g) issue_group(g);
+            int vb_base = 0;
+            for (int g = 0; g < n_groups; ++g) {
+                const int stage = g % S;
+                const int e0 = g * G;
+                if (e0 >= vb_base + 32) {
+                    vb = vb_nx;
+                    vb_base += 32;
+                    vb_nx = (vb_base + 32 + lane < n_ent) ? ld_once(val + P0 + vb_base + 32 + lane, pol) : 0.f;
+                }
+                mbar_wait(bars_u32 + stage * 8, (phase_bits >> stage) & 1u);
+                phase_bits ^= (1u << stage);
+                const int cnt = min(G, n_ent - e0);
+                const unsigned char* stage_base = my_ring + (size_t)(stage * G) * slot_bytes;
+                if (cnt == G && cur_end > P0 + e0 + G) {  // full group, no row end inside: check-free
+#pragma unroll
+                    for (int k = 0; k < G; ++k) {
+                        const float v = __shfl_sync(0xffffffffu, vb, (e0 - vb_base + k) & 31);
+#pragma unroll
+                        for (int s = 0; s < NSLOT; ++s) {
+                            if (fok[s]) {
+                                const float4 x = *reinterpret_cast<const float4*>(stage_base + (size_t)k * slot_bytes + (s * 32 + lane) * 16);
+                                acc[s].x = fmaf(v, x.x, acc[s].x);
+                                acc[s].y = fmaf(v, x.y, acc[s].y);
+                                acc[s].z = fmaf(v, x.z, acc[s].z);
+                                acc[s].w = fmaf(v, x.w, acc[s].w);
+                            }
+                        }
+                    }
+                } else {
+                    for (int k = 0; k < cnt; ++k) {
+                        const float v = __shfl_sync(0xffffffffu, vb, (e0 - vb_base + k) & 31);
+#pragma unroll
+                        for (int s = 0; s < NSLOT; ++s) {
+                            if (fok[s]) {
+                                const float4 x = *reinterpret_cast<const float4*>(stage_base + (size_t)k * slot_bytes + (s * 32 + lane) * 16);
+                                acc[s].x = fmaf(v, x.x, acc[s].x);
+                                acc[s].y = fmaf(v, x.y, acc[s].y);
+                                acc[s].z = fmaf(v, x.z, acc[s].z);
+                                acc[s].w = fmaf(v, x.w, acc[s].w);
+                            }
+                        }
+                        while (cur_row < b && cur_end == P0 + e0 + k + 1) flush_row(b);
+                    }
+                }
+                __syncwarp();  // every lane is done reading this stage before it is refilled
+                if (g + S < n_groups) issue_group(g + S);
+            }
+            a = b;
+        }
     }
 }
 
@@ -303,6 +572,65 @@ static int launch_cfg(const gnntf_csr_t* A, const float* B, int64_t ldb, const E
     return GNNTF_OK;
 }
 
+
+static int env_int(const char* name, int dflt) {
+    const char* e = getenv(name);
+    return e ? atoi(e) : dflt;
+}
+// Tuning knobs for A/B measurements (read once): GNNTF_SPMM_BULK=1 selects the TMA bulk-copy
+// kernel for wide rows (measured SLOWER than the register kernel on B200: 102 vs 61 ms on the
+// products shape — one 400-byte bulk copy costs ~23 cycles of TMA issue per SM — so it is off by
+// default), GNNTF_SPMM_ROWS the rows per chunk.
+static int bulk_mode() { static int v = env_int("GNNTF_SPMM_BULK", 0); return v; }
+static int bulk_rows_per_chunk() { static int v = std::max(1, std::min(31, env_int("GNNTF_SPMM_ROWS", 16))); return v; }
+
+template <int NSLOT, int G, int S>
+static int launch_bulk(const gnntf_csr_t* A, const float* B, int64_t ldb, const Epilogue& epi,
+                       cudaStream_t st) {
+    const int F = epi.F;
+    const int tile_floats = std::min(F, NSLOT * 128);
+    const unsigned gy = (unsigned)ceil_div(F, tile_floats);
+    const size_t per_warp = (size_t)S * G * tile_floats * 4;
+    const int thr = (A->n_long > 0) ? A->long_threshold : 0;
+    const int rows_per_chunk = bulk_rows_per_chunk();
+    auto go = [&](auto warps_tag) -> int {
+        constexpr int WARPS = decltype(warps_tag)::value;
+        const size_t smem = per_warp * WARPS + (size_t)WARPS * S * 8;
+        auto kern = spmm_bulk_kernel<NSLOT, G, S, WARPS>;
+        GNNTF_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        const int64_t chunks = ceil_div(A->n_rows, rows_per_chunk);
+        const int ctas_per_sm = (int)std::max<size_t>(1, std::min<size_t>(8, (size_t)(224 * 1024) / (smem + 1024)));
+        dim3 grid((unsigned)std::min<int64_t>(ceil_div(chunks, WARPS), (int64_t)kNumSMs * ctas_per_sm), gy);
+        kern<<<grid, WARPS * 32, smem, st>>>(A->row_ptr, A->col_idx, A->val, A->row_map, B, ldb,
+                                            (int)A->n_rows, thr, rows_per_chunk, tile_floats, epi);
+        GNNTF_LAUNCH_CHECK();
+        return GNNTF_OK;
+    };
+    if (A->n_rows > 0) {
+        int rc;
+        if (per_warp * 8 <= 110 * 1024) rc = go(std::integral_constant<int, 8>{});
+        else if (per_warp * 4 <= 110 * 1024) rc = go(std::integral_constant<int, 4>{});
+        else rc = go(std::integral_constant<int, 2>{});
+        if (rc != GNNTF_OK) return rc;
+    }
+    if (A->n_long > 0) {
+        constexpr int THREADS = 256;
+        const int ldp = (int)round_up(F, 4);
+        constexpr int RS = (NSLOT > 4) ? 4 : NSLOT;
+        const unsigned gy2 = (unsigned)ceil_div(F, 32 * RS * 4);
+        dim3 grid((unsigned)ceil_div(A->n_chunks, THREADS / 32), gy2);
+        spmm_chunk_kernel<4, RS, 32, (RS >= 4) ? 2 : 4, THREADS><<<grid, THREADS, 0, st>>>(
+            A->row_ptr, A->col_idx, A->val, B, ldb, A->chunk_row, A->chunk_begin, A->n_chunks,
+            A->chunk, A->partials, ldp, F);
+        GNNTF_LAUNCH_CHECK();
+        spmm_long_reduce_kernel<<<A->n_long, 128, 0, st>>>(A->long_row, A->long_first_chunk,
+                                                          A->long_n_chunks, A->row_map, A->partials,
+                                                          ldp, epi);
+        GNNTF_LAUNCH_CHECK();
+    }
+    return GNNTF_OK;
+}
+
 static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 int validate_csr(const gnntf_csr_t* A) {
@@ -340,6 +668,11 @@ int spmm_dispatch(const gnntf_csr_t* A, const float* B, int64_t ldb, Epilogue ep
     if (epi.ACC) v4 = v4 && (epi.ldacc % 4 == 0) && aligned16(epi.ACC);
     if (epi.keep) v4 = false;  // byte mask rows are F-strided: keep the scalar path
 
+    if (v4 && bulk_mode() && F >= 68) {
+        if (F <= 128) return launch_bulk<1, 8, 4>(A, B, ldb, epi, st);
+        if (F <= 256) return launch_bulk<2, 8, 2>(A, B, ldb, epi, st);
+        return launch_bulk<4, 4, 2>(A, B, ldb, epi, st);  // tiles of 512 floats over grid.y
+    }
     if (v4) {
         const int64_t slots = F / 4;
         if (slots <= 4) return launch_cfg<4, 1, 4>(A, B, ldb, epi, st);

@@ -187,7 +187,7 @@ class NormalizedAdjacency:
         self.deg = torch.zeros(n, **f32)
         self.dinv = torch.zeros(n, **f32)
         self.val = torch.empty(nnz, **f32)
-        want_T = self.has_mask and not base.directed
+        want_T = (self.has_mask or mode == "bipartite") and not base.directed  # row-only scaling is not symmetric
         self._val_T = torch.empty(nnz, **f32) if want_T else None
         self._values_coo = torch.empty(nnz, **f32)
         nat.check(L.gnntf_normalize_f32(nat.ptr(csr.row_ptr), nat.ptr(csr.col_idx), nat.ptr(raw_val),

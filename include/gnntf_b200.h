@@ -180,16 +180,13 @@ int gnntf_appnp_propagate_host_f32(const gnntf_csr_t* A, const float* H0_host, f
                                    int64_t F, double alpha, int K, void* stream);
 
 /* ------------------------------------------------------------------------------------------
- * Row-sharded multi-GPU helpers (contiguous node-range split; BASELINE north_star).
+ * Row-sharded multi-GPU helper (contiguous node-range split; BASELINE north_star).
  * Rank r owns rows [lo,hi).  Its local CSR addresses an EXTENDED feature matrix
  *   H_ext = [ n_local owned rows | n_halo rows received from peers ]
- * gnntf_csr_localize rewrites global column ids in place: c in [lo,hi) -> c-lo, otherwise
- * n_local + (rank of c in halo_cols, the sorted distinct remote columns; binary search).
- * gnntf_halo_pack_f32 gathers the rows a peer needs (send_idx, local row ids) into a dense send
- * buffer: out[i,:] = H[send_idx[i],:].
+ * (the column remapping and the per-peer send lists are host-side index logic, gnntf/dist.py).
+ * gnntf_halo_pack_f32 gathers the rows the peers need (send_idx: local row ids, grouped by
+ * destination rank) into the dense send buffer of the NCCL all-to-all: out[i,:] = H[send_idx[i],:].
  * ---------------------------------------------------------------------------------------- */
-int gnntf_csr_localize(int32_t* col_idx, int64_t nnz, int64_t lo, int64_t hi,
-                       const int32_t* halo_cols, int64_t n_halo, void* stream);
 int gnntf_halo_pack_f32(const float* H, int64_t ld, const int32_t* send_idx, int64_t n_send,
                         float* out, int64_t ldo, int64_t F, void* stream);
 

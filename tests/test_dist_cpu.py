@@ -1,0 +1,100 @@
+"""world_size-2 (and 3) gloo tests of the row-sharded path's host logic on CPU: nnz-balanced
+contiguous partition, column remapping to [owned | halo], the per-peer send lists agreed through
+all-to-all, the per-step halo exchange, and the interior/boundary row split.  The per-shard SpMM is
+played by the CPU oracle here (tests may use it as the checker); on a GPU box the same plan drives
+the native kernels (tests/test_gpu_parity.py::test_sharded_propagator_single_process)."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, n, edges, F, K, alpha, out_dir):
+    for p in (os.path.join(ROOT, "gnn-tf_b200"), os.path.join(ROOT, "oracle")):
+        sys.path.insert(0, p)
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import gnntf_oracle as oracle
+        from gnntf import dist as gdist
+        idx, val, _ = oracle.graph2adj_arrays(edges, None, n)
+        _, nv, _ = oracle.get_adjacency(idx, val, n)
+        row_ptr, col_idx, coo_pos, _ = oracle.csr_from_coo(idx, n)
+        plan = gdist.build_shard_plan(torch.from_numpy(row_ptr), torch.from_numpy(col_idx.astype(np.int32)),
+                                      torch.from_numpy(nv[coo_pos]), rank, world)
+        # structural checks
+        assert plan.bounds[0] == 0 and plan.bounds[-1] == n and plan.lo == plan.bounds[rank]
+        assert int(plan.interior_rows.numel() + plan.boundary_rows.numel()) == plan.n_local
+        assert sum(plan.recv_counts) == plan.n_halo and plan.recv_counts[rank] == 0
+        assert int(plan.send_idx.numel()) == sum(plan.send_counts)
+        if plan.n_halo:
+            hc = plan.halo_cols.numpy()
+            assert np.all(np.diff(hc) > 0) and np.all((hc < plan.lo) | (hc >= plan.hi))
+        if plan.send_idx.numel():
+            assert int(plan.send_idx.min()) >= 0 and int(plan.send_idx.max()) < plan.n_local
+        rp, col = plan.row_ptr.numpy(), plan.col_idx.numpy()
+        for r in plan.interior_rows.tolist():
+            assert np.all(col[rp[r]:rp[r + 1]] < plan.n_local)
+        for r in plan.boundary_rows.tolist():
+            assert np.any(col[rp[r]:rp[r + 1]] >= plan.n_local)
+        # emulate the propagation: per step pack -> all-to-all -> interior step -> boundary step
+        H0_full = np.random.default_rng(5).standard_normal((n, F)).astype(np.float32)
+        H0 = H0_full[plan.lo:plan.hi]
+        local_rows = np.repeat(np.arange(plan.n_local), np.diff(rp))
+        local_idx = np.stack([local_rows, col.astype(np.int64)], 1)
+        H = H0.copy()
+        for _ in range(K):
+            ext = np.zeros((plan.n_local + plan.n_halo, F), np.float32)
+            ext[:plan.n_local] = H
+            send = torch.from_numpy(H[plan.send_idx.long().numpy()].copy())
+            halo = torch.empty((plan.n_halo, F), dtype=torch.float32)
+            gdist.exchange_halo(plan, send, halo)
+            ext[plan.n_local:] = halo.numpy()
+            P = oracle.spmm_coo(local_idx, plan.val.numpy(), ext, n_rows=plan.n_local)
+            H = P * np.float32(1 - alpha) + H0 * np.float32(alpha)
+        expect = oracle.appnp_propagate(idx, val, n, H0_full, alpha, K)[-1][plan.lo:plan.hi]
+        oracle.assert_close(H, expect, what=f"rank {rank} shard")
+        # sub_csr of the boundary rows reproduces those rows
+        srp, scol, sval = gdist.sub_csr(plan.row_ptr, plan.col_idx, plan.val, plan.boundary_rows)
+        for i, r in enumerate(plan.boundary_rows.tolist()[:20]):
+            assert np.array_equal(scol[srp[i]:srp[i + 1]].numpy(), col[rp[r]:rp[r + 1]])
+        np.save(os.path.join(out_dir, f"ok_{rank}.npy"), np.array([plan.n_local, plan.n_halo]))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_sharded_plan_and_exchange_gloo(world, tmp_path):
+    rng = np.random.default_rng(0)
+    n, e, F, K = 400, 3000, 6, 4
+    edges = rng.integers(0, n, (e, 2))
+    edges[:200, 0] = 7  # a hub row so the nnz-balanced split differs from an equal-rows split
+    mp.spawn(_worker, args=(world, _free_port(), n, edges, F, K, 0.1, str(tmp_path)), nprocs=world, join=True)
+    sizes = [np.load(tmp_path / f"ok_{r}.npy") for r in range(world)]
+    assert sum(int(s[0]) for s in sizes) == n
+
+
+def test_partition_is_nnz_balanced():
+    sys.path.insert(0, os.path.join(ROOT, "gnn-tf_b200"))
+    from gnntf import dist as gdist
+    deg = torch.tensor([1000] + [1] * 999)
+    row_ptr = torch.zeros(1001, dtype=torch.int64)
+    torch.cumsum(deg, 0, out=row_ptr[1:])
+    b = gdist.partition_bounds(row_ptr, 4)
+    assert b[0] == 0 and b[-1] == 1000 and all(b[i] <= b[i + 1] for i in range(4))
+    loads = [int(row_ptr[b[i + 1]] - row_ptr[b[i]]) for i in range(4)]
+    assert max(loads) <= 1000 + 10 and sum(loads) == 1999       # the hub row is a shard of its own
+    assert gdist.partition_bounds(row_ptr, 1) == [0, 1000]

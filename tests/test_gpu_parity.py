@@ -437,3 +437,57 @@ def test_host_buffer_entry_matches_device_entry():
     out_host = gnntf.appnp_propagate_host(A, H0, 0.1, 10)
     out_dev = gnntf.appnp_propagate(A, H0.cuda(), 0.1, 10)
     assert torch.equal(out_host, out_dev.cpu())
+
+
+# ------------------------------------------------------------------------------------------
+# Row-sharded path: all ranks emulated in ONE process on one GPU (the exchange is a device copy),
+# native pack + interior/boundary step kernels with row_map.  The NCCL exchange itself is covered
+# by bench.py --gpus N on a multi-GPU box and by the gloo tests on CPU.
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("world", [2, 4])
+def test_sharded_propagator_emulated_ranks(world):
+    gnntf = _gnntf()
+    from gnntf import dist as gdist
+    n, edges = synthetic.shaped_edges("arxiv", seed=0, device="cuda", scale=0.2)
+    adj = gnntf.edges2adj(edges, None, n)
+    A = adj.normalized("symmetric")
+    F, K, a = 40, 10, 0.1
+    H0 = synthetic.features(n, F, 1, "cuda")
+    expect = gnntf.appnp_propagate(A, H0, a, K)
+    csr = A.csr
+    bounds = gdist.partition_bounds(csr.row_ptr, world)
+    first = [gdist.build_shard_plan(csr.row_ptr, csr.col_idx, A.val, r, 1 if world == 1 else world, peer_wants=lambda d: torch.empty(0))
+             for r in range(world)]          # pass 1: learn every rank's halo
+    plans = [gdist.build_shard_plan(csr.row_ptr, csr.col_idx, A.val, r, world,
+                                    peer_wants=lambda d, r=r: gdist.wanted_rows(first[d].halo_cols, bounds, r))
+             for r in range(world)]
+    assert sum(p.n_local for p in plans) == n and any(p.n_halo > 0 for p in plans)
+    props = []
+
+    def exchange(me, send_buf, halo_out):  # deliver every peer's packed rows for `me`
+        pass
+    props = [gdist.ShardedPropagator(adj, A, F, r, world, plan=plans[r], exchange=exchange) for r in range(world)]
+    # lock-step emulation of the K steps: pack on every rank, route, then compute on every rank
+    L, nat = gnntf._native.lib(), gnntf._native
+    bufs = [(p.buf[0], p.buf[1]) for p in props]
+    for p in props:
+        p.H0.copy_(H0[p.lo:p.hi])
+        p.buf[0][:p.n_local].copy_(p.H0)
+    for _ in range(K):
+        packed = []
+        for p, (src, dst) in zip(props, bufs):
+            if p.send_buf.shape[0]:
+                nat.check(L.gnntf_halo_pack_f32(nat.ptr(src), F, nat.ptr(p.plan.send_idx), p.send_buf.shape[0],
+                                                nat.ptr(p.send_buf), F, F, nat.stream_ptr()))
+            packed.append(torch.split(p.send_buf, p.plan.send_counts))
+        for r, (p, (src, dst)) in enumerate(zip(props, bufs)):
+            parts = [packed[o][r] for o in range(world)]                 # from owner o to me, in owner order
+            if p.n_halo:
+                src[p.n_local:].copy_(torch.cat(parts))
+        for p, (src, dst) in zip(props, bufs):
+            p._exchange = lambda *args: None
+            p._step(src, dst, a)
+        bufs = [(dst, src) for (src, dst) in bufs]
+    got = torch.cat([src[:p.n_local] for p, (src, dst) in zip(props, bufs)])
+    oracle.assert_close(_np(got), _np(expect), what="sharded vs single-GPU propagation")
+    assert props[0].launches_per_propagation(K) >= 2 * K
