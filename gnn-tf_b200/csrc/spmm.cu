@@ -58,10 +58,57 @@ __device__ __forceinline__ void apply_epilogue(const Epilogue& e, int64_t row, i
     }
 }
 
+// L2 eviction-policy helpers: data touched once per step (CSR arrays, the teleport term, the
+// output) is marked evict-first so it does not displace gathered feature rows from L2.
+__device__ __forceinline__ uint64_t policy_evict_first() {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ int ld_once(const int* p, uint64_t pol) {
+    int v;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.s32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(pol));
+    return v;
+}
+__device__ __forceinline__ float ld_once(const float* p, uint64_t pol) {
+    float v;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.f32 %0, [%1], %2;" : "=f"(v) : "l"(p), "l"(pol));
+    return v;
+}
+__device__ __forceinline__ float4 ld_once4(const float* p, uint64_t pol) {
+    float4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.f32 {%0,%1,%2,%3}, [%4], %5;"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+                 : "l"(p), "l"(pol));
+    return v;
+}
+__device__ __forceinline__ void st_once4(float* p, float4 v, uint64_t pol) {
+    asm volatile("st.global.L1::no_allocate.L2::cache_hint.v4.f32 [%0], {%1,%2,%3,%4}, %5;" ::"l"(p),
+                 "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "l"(pol)
+                 : "memory");
+}
+
+
 // ---------------------------------------------------------------------------------------------
-// Main kernel: GROUP lanes per sparse row, rows with deg > long_threshold are left to the
-// chunk path.  grid.x walks row blocks, grid.y walks feature tiles of GROUP*NSLOT*VEC floats.
+// Main kernel: GROUP lanes per sparse row; rows with deg > long_threshold are left to the piece
+// path.  A CTA walks kBlocksPerCta consecutive row blocks (fewer, longer-lived CTAs: the per-row
+// version launched 306 k CTAs on the products shape and ran at 47 % achieved occupancy);
+// grid.y walks feature tiles of GROUP*NSLOT*VEC floats.
+// A gather address costs one mad.wide.u32 (the first profile showed 28 executed instructions per
+// entry, most of them 64-bit address arithmetic, per-entry predicates and register zeroing); full
+// batches of UNROLL entries run predicate-free.
 // ---------------------------------------------------------------------------------------------
+constexpr int kBlocksPerCta = 8;
+
+// Address of a gathered row piece in ONE instruction: column ids are non-negative int32 and the
+// row pitch in bytes fits 32 bits, so base + c*pitch is exactly mad.wide.u32 (IMAD.WIDE.U32).
+template <int VEC>
+__device__ __forceinline__ Vec<VEC> gather_row(const float* lane_base, int c, uint32_t pitch_bytes) {
+    const float* p;
+    asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(p) : "r"(c), "r"(pitch_bytes), "l"(lane_base));
+    return Vec<VEC>::gather(p);
+}
+
 template <int VEC, int NSLOT, int GROUP, int UNROLL, int THREADS>
 __global__ void __launch_bounds__(THREADS)
 spmm_rows_kernel(const int* __restrict__ row_ptr, const int* __restrict__ col_idx,
@@ -69,84 +116,119 @@ spmm_rows_kernel(const int* __restrict__ row_ptr, const int* __restrict__ col_id
                  const float* __restrict__ B, int64_t ldb, int n_rows, int long_threshold, Epilogue epi) {
     constexpr int ROWS_PER_WARP = 32 / GROUP;
     constexpr int WARPS = THREADS / 32;
+    constexpr int ROWS_PER_BLOCK = WARPS * ROWS_PER_WARP;
     const int lane = threadIdx.x & 31;
     const int g = lane / GROUP;
     const int gl = lane % GROUP;
-    const int64_t row = ((int64_t)blockIdx.x * WARPS + (threadIdx.x >> 5)) * ROWS_PER_WARP + g;
     const int f_base = blockIdx.y * (GROUP * NSLOT * VEC);
     const int F = epi.F;
-
-    int start = 0, deg = 0;
-    bool mine = false;
-    if (row < n_rows) {
-        start = __ldg(row_ptr + row);
-        deg = __ldg(row_ptr + row + 1) - start;
-        mine = !(long_threshold > 0 && deg > long_threshold);
-        if (!mine) deg = 0;
-    }
-    int maxdeg = deg;
-    if (ROWS_PER_WARP > 1) {
-#pragma unroll
-        for (int o = GROUP; o < 32; o <<= 1) maxdeg = max(maxdeg, __shfl_xor_sync(0xffffffffu, maxdeg, o));
-    }
+    const uint64_t pol = policy_evict_first();
+    const uint32_t pitch = (uint32_t)ldb * 4u;
 
     int fo[NSLOT];
     bool fok[NSLOT];
+    const float* Bl[NSLOT];
 #pragma unroll
     for (int s = 0; s < NSLOT; ++s) {
         fo[s] = f_base + (s * GROUP + gl) * VEC;
         fok[s] = fo[s] < F;  // VEC == 4 implies F % 4 == 0, so the whole slot is in range
+        Bl[s] = B + (fok[s] ? fo[s] : 0);
     }
-    Vec<VEC> acc[NSLOT];
-#pragma unroll
-    for (int s = 0; s < NSLOT; ++s)
-#pragma unroll
-        for (int i = 0; i < VEC; ++i) acc[s].v[i] = 0.0f;
 
-    for (int off = 0; off < maxdeg; off += GROUP) {
-        int c = 0;
-        float v = 0.0f;
-        if (off + gl < deg) {
-            c = ld_stream(col_idx + start + off + gl);
-            v = ld_stream(val + start + off + gl);
+    for (int it = 0; it < kBlocksPerCta; ++it) {
+        const int64_t row = ((int64_t)blockIdx.x * kBlocksPerCta + it) * ROWS_PER_BLOCK +
+                            (threadIdx.x >> 5) * ROWS_PER_WARP + g;
+        if (row - g >= n_rows) break;  // warp-uniform: the whole warp is past the end
+        int start = 0, deg = 0;
+        bool mine = false;
+        if (row < n_rows) {
+            start = __ldg(row_ptr + row);
+            deg = __ldg(row_ptr + row + 1) - start;
+            mine = !(long_threshold > 0 && deg > long_threshold);
+            if (!mine) deg = 0;
         }
-        const int lim = min(GROUP, maxdeg - off);
-        for (int j = 0; j < lim; j += UNROLL) {
-            int cj[UNROLL];
-            float vj[UNROLL];
+        int maxdeg = deg, mindeg = deg;
+        if (ROWS_PER_WARP > 1) {
 #pragma unroll
-            for (int u = 0; u < UNROLL; ++u) {
-                cj[u] = __shfl_sync(0xffffffffu, c, j + u, GROUP);
-                vj[u] = __shfl_sync(0xffffffffu, v, j + u, GROUP);
+            for (int o = GROUP; o < 32; o <<= 1) {
+                maxdeg = max(maxdeg, __shfl_xor_sync(0xffffffffu, maxdeg, o));
+                mindeg = min(mindeg, __shfl_xor_sync(0xffffffffu, mindeg, o));
             }
-            Vec<VEC> x[UNROLL][NSLOT];
-#pragma unroll
-            for (int u = 0; u < UNROLL; ++u) {
-                const bool live = (j + u < GROUP) && (off + j + u < deg);
-                const float* src = B + (int64_t)cj[u] * ldb;
-#pragma unroll
-                for (int s = 0; s < NSLOT; ++s) {
-                    if (live && fok[s]) {
-                        x[u][s] = Vec<VEC>::gather(src + fo[s]);
-                    } else {
-#pragma unroll
-                        for (int i = 0; i < VEC; ++i) x[u][s].v[i] = 0.0f;
-                    }
-                }
-            }
-#pragma unroll
-            for (int u = 0; u < UNROLL; ++u)
-#pragma unroll
-                for (int s = 0; s < NSLOT; ++s)
-#pragma unroll
-                    for (int i = 0; i < VEC; ++i) acc[s].v[i] = fmaf(vj[u], x[u][s].v[i], acc[s].v[i]);
         }
-    }
-    if (mine) {
-        const int64_t out_row = row_map ? (int64_t)__ldg(row_map + row) : row;
+        Vec<VEC> acc[NSLOT];
 #pragma unroll
         for (int s = 0; s < NSLOT; ++s)
-            if (fok[s]) apply_epilogue<VEC>(epi, out_row, fo[s], acc[s]);
+#pragma unroll
+            for (int i = 0; i < VEC; ++i) acc[s].v[i] = 0.0f;
+
+        for (int off = 0; off < maxdeg; off += GROUP) {
+            int c = 0;
+            float v = 0.0f;
+            if (off + gl < deg) {
+                c = ld_once(col_idx + start + off + gl, pol);
+                v = ld_once(val + start + off + gl, pol);
+            }
+            const int lim = min(GROUP, maxdeg - off);
+            const int full = min(GROUP, mindeg - off);  // entries every group of the warp still has
+            int j = 0;
+            for (; j + UNROLL <= full; j += UNROLL) {    // predicate-free batches
+                int cj[UNROLL];
+                float vj[UNROLL];
+#pragma unroll
+                for (int u = 0; u < UNROLL; ++u) {
+                    cj[u] = __shfl_sync(0xffffffffu, c, j + u, GROUP);
+                    vj[u] = __shfl_sync(0xffffffffu, v, j + u, GROUP);
+                }
+                Vec<VEC> x[UNROLL][NSLOT];
+#pragma unroll
+                for (int u = 0; u < UNROLL; ++u)
+#pragma unroll
+                    for (int s = 0; s < NSLOT; ++s)
+                        if (fok[s]) x[u][s] = gather_row<VEC>(Bl[s], cj[u], pitch);
+#pragma unroll
+                for (int u = 0; u < UNROLL; ++u)
+#pragma unroll
+                    for (int s = 0; s < NSLOT; ++s)
+                        if (fok[s])
+#pragma unroll
+                            for (int i = 0; i < VEC; ++i) acc[s].v[i] = fmaf(vj[u], x[u][s].v[i], acc[s].v[i]);
+            }
+            for (; j < lim; j += UNROLL) {               // ragged tail: per-entry predicates
+                int cj[UNROLL];
+                float vj[UNROLL];
+#pragma unroll
+                for (int u = 0; u < UNROLL; ++u) {
+                    cj[u] = __shfl_sync(0xffffffffu, c, j + u, GROUP);
+                    vj[u] = __shfl_sync(0xffffffffu, v, j + u, GROUP);
+                }
+                Vec<VEC> x[UNROLL][NSLOT];
+#pragma unroll
+                for (int u = 0; u < UNROLL; ++u) {
+                    const bool live = (j + u < GROUP) && (off + j + u < deg);
+#pragma unroll
+                    for (int s = 0; s < NSLOT; ++s) {
+                        if (live && fok[s]) {
+                            x[u][s] = gather_row<VEC>(Bl[s], cj[u], pitch);
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < VEC; ++i) x[u][s].v[i] = 0.0f;
+                        }
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < UNROLL; ++u)
+#pragma unroll
+                    for (int s = 0; s < NSLOT; ++s)
+#pragma unroll
+                        for (int i = 0; i < VEC; ++i) acc[s].v[i] = fmaf(vj[u], x[u][s].v[i], acc[s].v[i]);
+            }
+        }
+        if (mine) {
+            const int64_t out_row = row_map ? (int64_t)__ldg(row_map + row) : row;
+#pragma unroll
+            for (int s = 0; s < NSLOT; ++s)
+                if (fok[s]) apply_epilogue<VEC>(epi, out_row, fo[s], acc[s]);
+        }
     }
 }
 
@@ -201,34 +283,6 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
                  "l"(src), "r"(bytes), "r"(bar)
                  : "memory");
 }
-__device__ __forceinline__ uint64_t policy_evict_first() {
-    uint64_t pol;
-    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
-    return pol;
-}
-__device__ __forceinline__ int ld_once(const int* p, uint64_t pol) {
-    int v;
-    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.s32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(pol));
-    return v;
-}
-__device__ __forceinline__ float ld_once(const float* p, uint64_t pol) {
-    float v;
-    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.f32 %0, [%1], %2;" : "=f"(v) : "l"(p), "l"(pol));
-    return v;
-}
-__device__ __forceinline__ float4 ld_once4(const float* p, uint64_t pol) {
-    float4 v;
-    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.f32 {%0,%1,%2,%3}, [%4], %5;"
-                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
-                 : "l"(p), "l"(pol));
-    return v;
-}
-__device__ __forceinline__ void st_once4(float* p, float4 v, uint64_t pol) {
-    asm volatile("st.global.L1::no_allocate.L2::cache_hint.v4.f32 [%0], {%1,%2,%3,%4}, %5;" ::"l"(p),
-                 "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "l"(pol)
-                 : "memory");
-}
-
 // Epilogue with the teleport row already in registers and evict-first stores; the rarely used
 // dropout-mask / backward-accumulate variants go through the generic path.
 __device__ __forceinline__ void epilogue_fast(const Epilogue& e, int64_t row, int f, const float4& a,
@@ -551,7 +605,7 @@ static int launch_cfg(const gnntf_csr_t* A, const float* B, int64_t ldb, const E
     const unsigned gy = (unsigned)ceil_div(F, tile);
     const int thr = (A->n_long > 0) ? A->long_threshold : 0;
     if (A->n_rows > 0) {
-        dim3 grid((unsigned)ceil_div(A->n_rows, ROWS_PER_CTA), gy);
+        dim3 grid((unsigned)ceil_div(A->n_rows, (int64_t)ROWS_PER_CTA * kBlocksPerCta), gy);
         spmm_rows_kernel<VEC, NSLOT, GROUP, UNROLL, THREADS><<<grid, THREADS, 0, st>>>(
             A->row_ptr, A->col_idx, A->val, A->row_map, B, ldb, (int)A->n_rows, thr, epi);
         GNNTF_LAUNCH_CHECK();
@@ -657,6 +711,7 @@ int spmm_dispatch(const gnntf_csr_t* A, const float* B, int64_t ldb, Epilogue ep
     if (F < 0 || F > 0x7fffffff) return GNNTF_E_SIZE;
     if (A->n_rows == 0 || F == 0) return GNNTF_OK;
     if (B == nullptr) return GNNTF_E_NULL;
+    if (ldb >= (1LL << 30)) return GNNTF_E_SIZE;  // row pitch in bytes must fit 32 bits
     if (ldb < F || (epi.C && epi.ldc < F) || (epi.H0 && epi.ldh < F) || (epi.ACC && epi.ldacc < F))
         return GNNTF_E_SIZE;
     epi.B = B;
