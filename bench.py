@@ -49,6 +49,16 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def measured_traffic(args, F):
+    """ncu-measured DRAM bytes per launch of the dominant kernel for this workload, if one was captured."""
+    path = os.path.join(ROOT, "profiles", "traffic.json")
+    if not os.path.exists(path) or args.scale != 1.0:
+        return None
+    with open(path) as f:
+        entry = json.load(f).get(f"{args.workload}/{args.ordering}/{F}")
+    return entry["dram_bytes_per_launch"] if entry else None
+
+
 def step_bytes(n, nnz, F):
     """Algorithmic bytes of one fused APPNP step: int32 col + fp32 val per entry,
     int32 row_ptr, read H_k, read H0, write H_{k+1}; every array touched once."""
@@ -219,10 +229,13 @@ def gpu_arm(args):
     nnz = adj.csr.nnz
     log(f"[build] graph2adj + CSR + normalise: {build_s * 1e3:.1f} ms (nnz={nnz}, long rows={adj.csr.n_long}, pieces={adj.csr.n_chunks})")
     H0 = synthetic.features(n, F, seed=1, device=dev)
+    if F % 4:  # class-width matrices (7, 47): run 16-byte-aligned rows, as gnntf.appnp_propagate does
+        H0, _ = ops._pad4(H0)
+    F_run = H0.shape[1]
 
     if world > 1:
         from gnntf import dist as gdist
-        prop = gdist.ShardedPropagator(adj, A, F, rank, world)
+        prop = gdist.ShardedPropagator(adj, A, F_run, rank, world)
         H0_local = H0[prop.lo:prop.hi].contiguous()
         run = lambda: prop.propagate(H0_local, ALPHA, K_ITER)  # noqa: E731
         launches_per_step = prop.launches_per_propagation(K_ITER)
@@ -272,12 +285,12 @@ def gpu_arm(args):
         result = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic", "config": config_dict(args, n, E, nnz, F),
+            "dtype": "f32", "data": "synthetic", "config": dict(config_dict(args, n, E, nnz, F), padded_features=F_run),
             "propagation_ms": {"mean": ms_per_step, "min": float(per_step_ms.min().item()),
                                "median": float(per_step_ms.median().item())},
             "clocks": clocks, "gpu_launches": launches_per_step * args.steps,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                         "traffic": None, "peak_source": peak_src, "frac_of_nominal_8TBs": achieved / 8000.0,
+                         "traffic": measured_traffic(args, F), "peak_source": peak_src, "frac_of_nominal_8TBs": achieved / 8000.0,
                          "kernel": "fused APPNP step (spmm_rows_kernel + long-row pieces/reduce)",
                          "algorithmic_bytes_per_launch": bstep,
                          "avg_launch_ms": ms_per_step / K_ITER,

@@ -91,14 +91,13 @@ __device__ __forceinline__ void st_once4(float* p, float4 v, uint64_t pol) {
 
 // ---------------------------------------------------------------------------------------------
 // Main kernel: GROUP lanes per sparse row; rows with deg > long_threshold are left to the piece
-// path.  A CTA walks kBlocksPerCta consecutive row blocks (fewer, longer-lived CTAs: the per-row
+// path.  A CTA walks blocks_per_cta consecutive row blocks (fewer, longer-lived CTAs: the per-row
 // version launched 306 k CTAs on the products shape and ran at 47 % achieved occupancy);
 // grid.y walks feature tiles of GROUP*NSLOT*VEC floats.
 // A gather address costs one mad.wide.u32 (the first profile showed 28 executed instructions per
 // entry, most of them 64-bit address arithmetic, per-entry predicates and register zeroing); full
 // batches of UNROLL entries run predicate-free.
 // ---------------------------------------------------------------------------------------------
-constexpr int kBlocksPerCta = 8;
 
 // Address of a gathered row piece in ONE instruction: column ids are non-negative int32 and the
 // row pitch in bytes fits 32 bits, so base + c*pitch is exactly mad.wide.u32 (IMAD.WIDE.U32).
@@ -109,21 +108,30 @@ __device__ __forceinline__ Vec<VEC> gather_row(const float* lane_base, int c, ui
     return Vec<VEC>::gather(p);
 }
 
-template <int VEC, int NSLOT, int GROUP, int UNROLL, int THREADS>
-__global__ void __launch_bounds__(THREADS)
+template <int VEC, int NSLOT, int GROUP, int UNROLL, int THREADS, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB)
 spmm_rows_kernel(const int* __restrict__ row_ptr, const int* __restrict__ col_idx,
                  const float* __restrict__ val, const int* __restrict__ row_map,
-                 const float* __restrict__ B, int64_t ldb, int n_rows, int long_threshold, Epilogue epi) {
+                 const float* __restrict__ B, int64_t ldb, int n_rows, int long_threshold,
+                 int blocks_per_cta, Epilogue epi) {
+    static_assert(UNROLL % 2 == 0 && GROUP % 2 == 0, "entries are read back two at a time");
     constexpr int ROWS_PER_WARP = 32 / GROUP;
     constexpr int WARPS = THREADS / 32;
     constexpr int ROWS_PER_BLOCK = WARPS * ROWS_PER_WARP;
+    // (col,val) pairs of the current 32 entries of this warp, broadcast through shared memory:
+    // one LDS.128 delivers two entries to every lane (0.5 L1 wavefronts per entry; the shuffle
+    // pair it replaces cost 2 wavefronts and was a third of the L1 data-pipe traffic, profiles/r1/02)
+    __shared__ __align__(16) int2 cv_smem[WARPS][32 + UNROLL];
     const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
     const int g = lane / GROUP;
     const int gl = lane % GROUP;
     const int f_base = blockIdx.y * (GROUP * NSLOT * VEC);
     const int F = epi.F;
     const uint64_t pol = policy_evict_first();
     const uint32_t pitch = (uint32_t)ldb * 4u;
+    int2* cv = cv_smem[warp];
+    const int2* cv_group = cv + g * GROUP;
 
     int fo[NSLOT];
     bool fok[NSLOT];
@@ -134,10 +142,10 @@ spmm_rows_kernel(const int* __restrict__ row_ptr, const int* __restrict__ col_id
         fok[s] = fo[s] < F;  // VEC == 4 implies F % 4 == 0, so the whole slot is in range
         Bl[s] = B + (fok[s] ? fo[s] : 0);
     }
+    if (lane < UNROLL) cv[32 + lane] = make_int2(0, 0);  // padding read (never used) by ragged tails
 
-    for (int it = 0; it < kBlocksPerCta; ++it) {
-        const int64_t row = ((int64_t)blockIdx.x * kBlocksPerCta + it) * ROWS_PER_BLOCK +
-                            (threadIdx.x >> 5) * ROWS_PER_WARP + g;
+    for (int it = 0; it < blocks_per_cta; ++it) {
+        const int64_t row = ((int64_t)blockIdx.x * blocks_per_cta + it) * ROWS_PER_BLOCK + warp * ROWS_PER_WARP + g;
         if (row - g >= n_rows) break;  // warp-uniform: the whole warp is past the end
         int start = 0, deg = 0;
         bool mine = false;
@@ -168,6 +176,9 @@ spmm_rows_kernel(const int* __restrict__ row_ptr, const int* __restrict__ col_id
                 c = ld_once(col_idx + start + off + gl, pol);
                 v = ld_once(val + start + off + gl, pol);
             }
+            __syncwarp();  // everyone is done reading the previous batch
+            cv[lane] = make_int2(c, __float_as_int(v));
+            __syncwarp();
             const int lim = min(GROUP, maxdeg - off);
             const int full = min(GROUP, mindeg - off);  // entries every group of the warp still has
             int j = 0;
@@ -175,9 +186,10 @@ spmm_rows_kernel(const int* __restrict__ row_ptr, const int* __restrict__ col_id
                 int cj[UNROLL];
                 float vj[UNROLL];
 #pragma unroll
-                for (int u = 0; u < UNROLL; ++u) {
-                    cj[u] = __shfl_sync(0xffffffffu, c, j + u, GROUP);
-                    vj[u] = __shfl_sync(0xffffffffu, v, j + u, GROUP);
+                for (int u = 0; u < UNROLL; u += 2) {
+                    const int4 e = *reinterpret_cast<const int4*>(cv_group + j + u);
+                    cj[u] = e.x; vj[u] = __int_as_float(e.y);
+                    cj[u + 1] = e.z; vj[u + 1] = __int_as_float(e.w);
                 }
                 Vec<VEC> x[UNROLL][NSLOT];
 #pragma unroll
@@ -197,9 +209,10 @@ spmm_rows_kernel(const int* __restrict__ row_ptr, const int* __restrict__ col_id
                 int cj[UNROLL];
                 float vj[UNROLL];
 #pragma unroll
-                for (int u = 0; u < UNROLL; ++u) {
-                    cj[u] = __shfl_sync(0xffffffffu, c, j + u, GROUP);
-                    vj[u] = __shfl_sync(0xffffffffu, v, j + u, GROUP);
+                for (int u = 0; u < UNROLL; u += 2) {
+                    const int4 e = *reinterpret_cast<const int4*>(cv_group + j + u);
+                    cj[u] = e.x; vj[u] = __int_as_float(e.y);
+                    cj[u + 1] = e.z; vj[u + 1] = __int_as_float(e.w);
                 }
                 Vec<VEC> x[UNROLL][NSLOT];
 #pragma unroll
@@ -216,11 +229,14 @@ spmm_rows_kernel(const int* __restrict__ row_ptr, const int* __restrict__ col_id
                     }
                 }
 #pragma unroll
-                for (int u = 0; u < UNROLL; ++u)
+                for (int u = 0; u < UNROLL; ++u) {
+                    const bool live = (j + u < GROUP) && (off + j + u < deg);
 #pragma unroll
                     for (int s = 0; s < NSLOT; ++s)
 #pragma unroll
-                        for (int i = 0; i < VEC; ++i) acc[s].v[i] = fmaf(vj[u], x[u][s].v[i], acc[s].v[i]);
+                        for (int i = 0; i < VEC; ++i)
+                            acc[s].v[i] = live ? fmaf(vj[u], x[u][s].v[i], acc[s].v[i]) : acc[s].v[i];
+                }
             }
         }
         if (mine) {
@@ -594,6 +610,19 @@ spmm_long_reduce_kernel(const int* __restrict__ long_row, const int* __restrict_
 // ---------------------------------------------------------------------------------------------
 // Host-side dispatch
 // ---------------------------------------------------------------------------------------------
+static int env_int(const char* name, int dflt) {
+    const char* e = getenv(name);
+    return e ? atoi(e) : dflt;
+}
+// Tuning knobs for A/B measurements (read once): GNNTF_SPMM_BULK=1 selects the TMA bulk-copy
+// kernel for wide rows (measured SLOWER than the register kernel on B200: 102 vs 61 ms on the
+// products shape — one 400-byte bulk copy costs ~23 cycles of TMA issue per SM — so it is off by
+// default), GNNTF_SPMM_ROWS the rows per chunk.
+static int rows_minb() { static int v = env_int("GNNTF_SPMM_MINB", 5); return v; }
+static int rows_blocks_per_cta() { static int v = std::max(1, env_int("GNNTF_SPMM_BPC", 8)); return v; }
+static int bulk_mode() { static int v = env_int("GNNTF_SPMM_BULK", 0); return v; }
+static int bulk_rows_per_chunk() { static int v = std::max(1, std::min(31, env_int("GNNTF_SPMM_ROWS", 16))); return v; }
+
 template <int VEC, int NSLOT, int GROUP>
 static int launch_cfg(const gnntf_csr_t* A, const float* B, int64_t ldb, const Epilogue& epi,
                       cudaStream_t st) {
@@ -605,9 +634,20 @@ static int launch_cfg(const gnntf_csr_t* A, const float* B, int64_t ldb, const E
     const unsigned gy = (unsigned)ceil_div(F, tile);
     const int thr = (A->n_long > 0) ? A->long_threshold : 0;
     if (A->n_rows > 0) {
-        dim3 grid((unsigned)ceil_div(A->n_rows, (int64_t)ROWS_PER_CTA * kBlocksPerCta), gy);
-        spmm_rows_kernel<VEC, NSLOT, GROUP, UNROLL, THREADS><<<grid, THREADS, 0, st>>>(
-            A->row_ptr, A->col_idx, A->val, A->row_map, B, ldb, (int)A->n_rows, thr, epi);
+        // several row blocks per CTA once the grid is deep enough to keep every SM busy for many
+        // waves; small graphs (Cora: 43 row blocks) keep one block per CTA
+        const int64_t row_blocks = ceil_div(A->n_rows, ROWS_PER_CTA);
+        const int bpc = (int)std::max<int64_t>(1, std::min<int64_t>(rows_blocks_per_cta(), row_blocks / ((int64_t)kNumSMs * 5 * 4)));
+        dim3 grid((unsigned)ceil_div(A->n_rows, (int64_t)ROWS_PER_CTA * bpc), gy);
+        if (rows_minb() >= 6)
+            spmm_rows_kernel<VEC, NSLOT, GROUP, UNROLL, THREADS, 6><<<grid, THREADS, 0, st>>>(
+                A->row_ptr, A->col_idx, A->val, A->row_map, B, ldb, (int)A->n_rows, thr, bpc, epi);
+        else if (rows_minb() == 4)
+            spmm_rows_kernel<VEC, NSLOT, GROUP, UNROLL, THREADS, 4><<<grid, THREADS, 0, st>>>(
+                A->row_ptr, A->col_idx, A->val, A->row_map, B, ldb, (int)A->n_rows, thr, bpc, epi);
+        else
+            spmm_rows_kernel<VEC, NSLOT, GROUP, UNROLL, THREADS, 5><<<grid, THREADS, 0, st>>>(
+                A->row_ptr, A->col_idx, A->val, A->row_map, B, ldb, (int)A->n_rows, thr, bpc, epi);
         GNNTF_LAUNCH_CHECK();
     }
     if (A->n_long > 0) {
@@ -626,17 +666,6 @@ static int launch_cfg(const gnntf_csr_t* A, const float* B, int64_t ldb, const E
     return GNNTF_OK;
 }
 
-
-static int env_int(const char* name, int dflt) {
-    const char* e = getenv(name);
-    return e ? atoi(e) : dflt;
-}
-// Tuning knobs for A/B measurements (read once): GNNTF_SPMM_BULK=1 selects the TMA bulk-copy
-// kernel for wide rows (measured SLOWER than the register kernel on B200: 102 vs 61 ms on the
-// products shape — one 400-byte bulk copy costs ~23 cycles of TMA issue per SM — so it is off by
-// default), GNNTF_SPMM_ROWS the rows per chunk.
-static int bulk_mode() { static int v = env_int("GNNTF_SPMM_BULK", 0); return v; }
-static int bulk_rows_per_chunk() { static int v = std::max(1, std::min(31, env_int("GNNTF_SPMM_ROWS", 16))); return v; }
 
 template <int NSLOT, int G, int S>
 static int launch_bulk(const gnntf_csr_t* A, const float* B, int64_t ldb, const Epilogue& epi,

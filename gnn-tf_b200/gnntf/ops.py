@@ -36,6 +36,19 @@ def _dense(x, n_rows=None):
     return x
 
 
+def _pad4(x):
+    """Zero-pad the feature dimension to a multiple of 4 floats so rows are 16-byte aligned and the
+    kernels take the float4 path (class-width matrices: 7, 47 ...).  Padding columns stay zero
+    through SpMM / teleport / relu, so slicing the result back is exact."""
+    F = x.shape[1]
+    Fp = (F + 3) // 4 * 4
+    if Fp == F:
+        return x, F
+    out = torch.zeros((x.shape[0], Fp), dtype=x.dtype, device=x.device)
+    out[:, :F] = x
+    return out, F
+
+
 def _ld(x):
     return x.stride(0) if x.shape[0] > 1 else max(x.shape[1], x.stride(0))
 
@@ -149,14 +162,15 @@ def propagate_raw(adjs, H0, alpha, K, out=None, scratch=None):
 class _Propagate(torch.autograd.Function):
     @staticmethod
     def forward(ctx, adjs, H0, alpha, K):
-        H0 = H0.contiguous()
+        H0p, F = _pad4(H0.contiguous())
         ctx.adjs, ctx.alpha, ctx.K = adjs, alpha, K
-        return propagate_raw(adjs, H0, alpha, K)
+        out = propagate_raw(adjs, H0p, alpha, K)
+        return out if out.shape[1] == F else out[:, :F].contiguous()
 
     @staticmethod
     def backward(ctx, g):
         L = nat.lib()
-        g = g.contiguous()
+        g, F_orig = _pad4(g.contiguous())
         F, ld, K = g.shape[1], _ld(g), ctx.K
         adjs = ctx.adjs if isinstance(ctx.adjs, (list, tuple)) else [ctx.adjs] * K
         arr = _struct_array([a.struct_T(F) for a in adjs])
@@ -164,7 +178,7 @@ class _Propagate(torch.autograd.Function):
         scratch = torch.empty((2,) + tuple(g.shape), dtype=g.dtype, device=g.device) if K > 1 else None
         nat.check(L.gnntf_appnp_propagate_bwd_f32(arr, K, nat.ptr(g), nat.ptr(dH0), nat.ptr(scratch), ld, F,
                                                   float(ctx.alpha), nat.stream_ptr()), "appnp_propagate_bwd")
-        return None, dH0, None, None
+        return None, (dH0 if F == F_orig else dH0[:, :F_orig].contiguous()), None, None
 
 
 def appnp_propagate(adjs, H0, alpha=0.1, iterations=10):
