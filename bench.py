@@ -37,6 +37,16 @@ K_ITER = 10
 ALPHA = 0.1
 
 
+# stdout must carry exactly ONE JSON line: libraries write there too (NCCL prints its version banner
+# on stdout), so fd 1 is pointed at stderr for the whole run and the JSON goes to the saved fd.
+_REAL_STDOUT = os.dup(1)
+os.dup2(2, 1)
+
+
+def emit_json(obj):
+    os.write(_REAL_STDOUT, (json.dumps(obj) + "\n").encode())
+
+
 def log(*a):
     print(*a, file=sys.stderr, flush=True)
 
@@ -205,6 +215,7 @@ def dist_setup(n_gpus):
     if world > 1:
         torch.cuda.set_device(local)
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("TORCH_NCCL_HIGH_PRIORITY", "1")  # the halo exchange must not queue behind the SpMM grid
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     else:
         torch.cuda.set_device(0)
@@ -235,7 +246,8 @@ def gpu_arm(args):
 
     if world > 1:
         from gnntf import dist as gdist
-        prop = gdist.ShardedPropagator(adj, A, F_run, rank, world)
+        prop = gdist.ShardedPropagator(adj, A, F_run, rank, world, halves=args.halves or None)
+        log(f"[shard {rank}] rows {prop.lo}:{prop.hi} nnz {prop.nnz_local} halo rows {prop.n_halo} owned-column entries {prop.owned.nnz} halo-column entries {prop.halo_part.nnz} (rows {prop.halo_part.n}) parts {[p['F'] for p in prop.parts]}")
         H0_local = H0[prop.lo:prop.hi].contiguous()
         run = lambda: prop.propagate(H0_local, ALPHA, K_ITER)  # noqa: E731
         launches_per_step = prop.launches_per_propagation(K_ITER)
@@ -285,7 +297,8 @@ def gpu_arm(args):
         result = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic", "config": dict(config_dict(args, n, E, nnz, F), padded_features=F_run),
+            "dtype": "f32", "data": "synthetic", "config": dict(config_dict(args, n, E, nnz, F), padded_features=F_run,
+                           sharding=(f"contiguous node ranges balanced by nnz over {world} GPUs; halo rows by NCCL all-to-all" if world > 1 else "none")),
             "propagation_ms": {"mean": ms_per_step, "min": float(per_step_ms.min().item()),
                                "median": float(per_step_ms.median().item())},
             "clocks": clocks, "gpu_launches": launches_per_step * args.steps,
@@ -333,7 +346,7 @@ def gpu_arm(args):
                                   "host_cpus": os.cpu_count(), "wall_s": time.time() - t0}
     if rank == 0:
         os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
-        print(json.dumps(result), flush=True)
+        emit_json(result)
     if world > 1:
         torch.distributed.barrier()
         torch.distributed.destroy_process_group()
@@ -358,7 +371,7 @@ def reference_arm(args):
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "note": "the reference (TensorFlow) cannot be installed in this image; this is the oracle's C port of its "
                     "CPU path (COO-order single-threaded SpMM loop + teleport), timed on a bounded sample"}
-    print(json.dumps(line), flush=True)
+    emit_json(line)
 
 
 def main():
@@ -372,6 +385,7 @@ def main():
     ap.add_argument("--features", type=int, default=0, help="feature width (default: the shape's)")
     ap.add_argument("--scale", type=float, default=1.0, help="shrink the graph (tests only; 1.0 = BASELINE size)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--halves", type=int, default=0, help="multi-GPU: feature-column chains to pipeline (0 = default)")
     args = ap.parse_args()
     if args.impl == "reference":
         reference_arm(args)

@@ -47,7 +47,10 @@ __device__ __forceinline__ void apply_epilogue(const Epilogue& e, int64_t row, i
     if (e.C != nullptr) out.store(e.C + row * e.ldc + f);
     if (e.ACC != nullptr) {
         float* a = e.ACC + row * e.ldacc + f;
-        Vec<VEC> b = Vec<VEC>::stream(e.B + row * e.ldb + f);
+        Vec<VEC> b;
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) b.v[i] = 0.0f;
+        if (e.u != 0.0f) b = Vec<VEC>::stream(e.B + row * e.ldb + f);  // the dense operand's own row
         Vec<VEC> r;
 #pragma unroll
         for (int i = 0; i < VEC; ++i) {
@@ -869,5 +872,22 @@ extern "C" int gnntf_spmm_f32(const gnntf_csr_t* A, const float* B, int64_t ldb,
     e.F = (int)F;
     e.act = GNNTF_ACT_IDENTITY;
     if (F < 0 || F > 0x7fffffff) return GNNTF_E_SIZE;
+    return spmm_dispatch(A, B, ldb, e, (cudaStream_t)stream);
+}
+
+extern "C" int gnntf_spmm_acc_f32(const gnntf_csr_t* A, const float* B, int64_t ldb, float* C,
+                                  int64_t ldc, int64_t F, double scale, void* stream) {
+    if (C == nullptr && A != nullptr && A->n_rows > 0 && F > 0) return GNNTF_E_NULL;
+    if (F < 0 || F > 0x7fffffff) return GNNTF_E_SIZE;
+    Epilogue e{};
+    e.s = (float)scale;
+    e.act = GNNTF_ACT_IDENTITY;
+    e.F = (int)F;
+    e.C = nullptr;   // the product only feeds the accumulator
+    e.ACC = C;
+    e.ldacc = ldc;
+    e.u = 0.0f;
+    e.w = 1.0f;
+    e.acc_init = 0;
     return spmm_dispatch(A, B, ldb, e, (cudaStream_t)stream);
 }

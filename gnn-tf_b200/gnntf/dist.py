@@ -8,8 +8,12 @@ overlapped with the SpMM of the rows that need no halo.
 
   rank r owns rows [lo_r, hi_r);  its CSR addresses  H_ext = [ owned rows | halo rows ]
   step:  pack rows peers need (native kernel)  ->  all-to-all (NCCL over NVLink)      [comm]
-         fused APPNP step on INTERIOR rows (all columns owned)                        [compute, overlaps]
-         wait for the halo  ->  fused APPNP step on BOUNDARY rows
+         fused APPNP step of ALL rows over their OWNED columns (the bulk of the entries;
+         needs no halo)                                                               [compute, overlaps]
+         wait for the halo  ->  accumulate the HALO-column entries of the boundary rows
+(the shard's CSR is split by column, not by row: on power-law graphs almost every row touches
+some remote column, so a row split leaves nothing to overlap with — measured 6 % interior rows
+on the products shape at 2 GPUs).
 
 :func:`build_shard_plan` is pure index logic on torch tensors (device-agnostic, covered by
 world-size-2 gloo tests on CPU); :class:`ShardedPropagator` binds it to the native kernels.
@@ -112,6 +116,28 @@ def wanted_rows(halo_cols, bounds, owner_rank):
     return (sel - lo).to(torch.int32)
 
 
+def split_by_column(row_ptr, col_idx, val, n_local):
+    """Split a shard-local CSR into the entries over OWNED columns (all rows, identity row map) and
+    the entries over HALO columns (compact CSR over the rows that have any, plus those row ids).
+    Entry order inside a row is preserved in both parts."""
+    dev = row_ptr.device
+    n = row_ptr.numel() - 1
+    is_halo = col_idx >= n_local
+    csum = torch.zeros(col_idx.numel() + 1, dtype=torch.int64, device=dev)
+    torch.cumsum(is_halo.to(torch.int64), 0, out=csum[1:])
+    rp = row_ptr.long()
+    halo_deg = csum[rp[1:]] - csum[rp[:-1]]
+    deg = rp[1:] - rp[:-1]
+    own_rp = torch.zeros(n + 1, dtype=torch.int64, device=dev)
+    torch.cumsum(deg - halo_deg, 0, out=own_rp[1:])
+    own = (own_rp.to(torch.int32).contiguous(), col_idx[~is_halo].contiguous(), val[~is_halo].contiguous())
+    rows = torch.nonzero(halo_deg > 0).flatten().to(torch.int32).contiguous()
+    halo_rp = torch.zeros(rows.numel() + 1, dtype=torch.int64, device=dev)
+    torch.cumsum(halo_deg[rows.long()], 0, out=halo_rp[1:])
+    halo = (halo_rp.to(torch.int32).contiguous(), col_idx[is_halo].contiguous(), val[is_halo].contiguous())
+    return own, halo, rows
+
+
 def sub_csr(row_ptr, col_idx, val, rows):
     """Compact CSR of a row subset (``rows`` int32 ascending): (row_ptr, col_idx, val)."""
     dev = row_ptr.device
@@ -136,72 +162,135 @@ def exchange_halo(plan: ShardPlan, send_buf, halo_out, group=None, async_op=Fals
                                   input_split_sizes=plan.send_counts, group=group, async_op=async_op)
 
 
-class ShardedPropagator:
-    """APPNP K-step propagation of one shard on one GPU (see module docstring)."""
+def p_world_gt1(world):
+    return world > 1 and torch.cuda.is_available()
 
-    def __init__(self, adj, A, F, rank, world, group=None, plan=None, exchange=None):
+
+class _EventWork:
+    """``work.wait()`` for the single-process emulation hook: the compute stream waits for an event."""
+
+    def __init__(self, event):
+        self.event = event
+
+    def wait(self):
+        torch.cuda.current_stream().wait_event(self.event)
+
+
+class ShardedPropagator:
+    """APPNP K-step propagation of one shard on one GPU (see module docstring).
+
+    ``halves=2`` (default when world > 1) runs the propagation as two independent chains over the
+    two halves of the feature columns (columns propagate independently through
+    H <- (1-a)·Â·H + a·H0), software-pipelined so that the halo exchange of one half for step k+1
+    is in flight while the other half computes step k.  Costs a second pass over the CSR and
+    narrower gathers (~1.2x compute), hides most of the exchange."""
+
+    def __init__(self, adj, A, F, rank, world, group=None, plan=None, exchange=None, halves=None):
         from . import _native as nat
         from .sparse import CsrStructure
         self.nat = nat
         self.group, self.F = group, int(F)
         self._exchange = exchange  # test hook: single-process emulation of the all-to-all
+        self.comm_stream = torch.cuda.Stream(priority=-1) if p_world_gt1(world) else None
         csr = A.csr
         self.plan = p = plan if plan is not None else build_shard_plan(csr.row_ptr, csr.col_idx, A.val, rank, world, group)
         self.lo, self.hi, self.n_local, self.n_halo = p.lo, p.hi, p.n_local, p.n_halo
         self.nnz_local = int(p.col_idx.numel())
         dev = p.row_ptr.device
 
-        def make(rows):
-            rp, col, val = sub_csr(p.row_ptr, p.col_idx, p.val, rows)
-            st = CsrStructure(int(rows.numel()), rp, col, None)
-            st.row_map = rows.contiguous()
-            return st, val
-        self.interior, self.interior_val = make(p.interior_rows)
-        self.boundary, self.boundary_val = make(p.boundary_rows)
-        n_ext = self.n_local + self.n_halo
-        self.buf = [torch.zeros((n_ext, self.F), dtype=torch.float32, device=dev) for _ in range(2)]
-        self.send_buf = torch.empty((int(sum(p.send_counts)), self.F), dtype=torch.float32, device=dev)
-        self.H0 = torch.empty((self.n_local, self.F), dtype=torch.float32, device=dev)
+        (o_rp, o_col, o_val), (h_rp, h_col, h_val), h_rows = split_by_column(p.row_ptr, p.col_idx, p.val, self.n_local)
+        self.owned, self.owned_val = CsrStructure(self.n_local, o_rp, o_col, None), o_val
+        self.halo_part, self.halo_val = CsrStructure(int(h_rows.numel()), h_rp, h_col, None), h_val
+        self.halo_part.row_map = h_rows
+        self.interior, self.boundary = self.owned, self.halo_part  # (names kept for reports: pass 1 / pass 2)
+        if halves is None:
+            halves = 1  # column-half pipelining measured slower than the column split at N=2 (DESIGN.md §6)
+        first = ((self.F + halves - 1) // halves + 3) // 4 * 4 if halves > 1 else self.F
+        widths = [first, self.F - first] if halves > 1 and self.F - first > 0 else [self.F]
+        n_ext, n_send = self.n_local + self.n_halo, int(sum(p.send_counts))
+        self.parts, col0 = [], 0
+        for w in widths:
+            self.parts.append(dict(F=w, col0=col0,
+                                   buf=[torch.zeros((n_ext, w), dtype=torch.float32, device=dev) for _ in range(2)],
+                                   send=torch.empty((n_send, w), dtype=torch.float32, device=dev),
+                                   H0=torch.empty((self.n_local, w), dtype=torch.float32, device=dev), work=None))
+            col0 += w
+        # single-part aliases (tests and the emulation hook address them directly)
+        self.buf, self.send_buf, self.H0 = self.parts[0]["buf"], self.parts[0]["send"], self.parts[0]["H0"]
 
     def launches_per_propagation(self, K):
-        per_step = 1  # pack
-        for st in (self.interior, self.boundary):
-            if st.n > 0:
+        per_step = 1 if self.plan.world > 1 else 0  # pack
+        for st in (self.owned, self.halo_part):
+            if st.n > 0 and st.nnz > 0 or st is self.owned:
                 per_step += 3 if st.n_long > 0 else 1
-        return K * per_step
+        return K * per_step * len(self.parts)
+
+    # -- one half: exchange and compute -----------------------------------------------------
+    def _start_exchange(self, part, src):
+        """Pack + all-to-all of this part's halo rows on the comm stream, ordered after everything
+        already enqueued on the compute stream (the step that produced ``src``)."""
+        nat, L, p = self.nat, self.nat.lib(), self.plan
+        part["work"] = None
+        if p.world == 1:
+            return
+        F = part["F"]
+        ready = torch.cuda.Event()
+        ready.record()                                   # src complete on the compute stream
+        with torch.cuda.stream(self.comm_stream):
+            self.comm_stream.wait_event(ready)
+            if part["send"].shape[0] > 0:
+                nat.check(L.gnntf_halo_pack_f32(nat.ptr(src), F, nat.ptr(p.send_idx), part["send"].shape[0],
+                                                nat.ptr(part["send"]), F, F, nat.stream_ptr()), "halo_pack")
+            if self._exchange is not None:
+                self._exchange(self, part["send"], src[self.n_local:])
+                done = torch.cuda.Event()
+                done.record()
+                part["work"] = _EventWork(done)
+            else:
+                part["work"] = exchange_halo(p, part["send"], src[self.n_local:], self.group, async_op=True)
+
+    def _compute(self, part, src, dst, alpha):
+        nat, L = self.nat, self.nat.lib()
+        F, st = part["F"], self.nat.stream_ptr()
+        # pass 1: every row over its owned columns, full epilogue (teleport term included)
+        s1 = self.owned.struct(self.owned_val, F)
+        nat.check(L.gnntf_appnp_step_f32(ctypes.byref(s1), nat.ptr(src), nat.ptr(part["H0"]), nat.ptr(dst), F, F,
+                                         float(alpha), None, 1.0, nat.ACT_IDENTITY, st), "appnp_step")
+        if part["work"] is not None:
+            part["work"].wait()  # the compute stream waits for this part's halo rows
+            part["work"] = None
+        # pass 2: dst[boundary rows] += (1-a) * (entries over halo columns) . H_halo
+        if self.halo_part.n > 0:
+            s2 = self.halo_part.struct(self.halo_val, F)
+            nat.check(L.gnntf_spmm_acc_f32(ctypes.byref(s2), nat.ptr(src), F, nat.ptr(dst), F, F, 1.0 - float(alpha), st),
+                      "spmm_acc")
 
     def _step(self, src, dst, alpha):
-        nat, L, p = self.nat, self.nat.lib(), self.plan
-        F, st = self.F, self.nat.stream_ptr()
-        work = None
-        if p.world > 1:
-            if self.send_buf.shape[0] > 0:
-                nat.check(L.gnntf_halo_pack_f32(nat.ptr(src), F, nat.ptr(p.send_idx), self.send_buf.shape[0],
-                                                nat.ptr(self.send_buf), F, F, st), "halo_pack")
-            if self._exchange is not None:
-                self._exchange(self, self.send_buf, src[self.n_local:])
-            else:
-                work = exchange_halo(p, self.send_buf, src[self.n_local:], self.group, async_op=True)
-        for structure, val, wait in ((self.interior, self.interior_val, False), (self.boundary, self.boundary_val, True)):
-            if wait and work is not None:
-                work.wait()  # the compute stream waits for the halo rows
-            if structure.n == 0:
-                continue
-            s = structure.struct(val, F)
-            nat.check(L.gnntf_appnp_step_f32(ctypes.byref(s), nat.ptr(src), nat.ptr(self.H0), nat.ptr(dst), F, F,
-                                             float(alpha), None, 1.0, nat.ACT_IDENTITY, st), "appnp_step")
-        if work is not None and self.boundary.n == 0:
-            work.wait()
+        """One un-pipelined step of the first part (kept for the single-process emulation test)."""
+        self._start_exchange(self.parts[0], src)
+        self._compute(self.parts[0], src, dst, alpha)
 
     def propagate(self, H0_local, alpha=0.1, iterations=10):
-        """K fused steps on this shard; returns this rank's rows of H_K ([n_local, F] view)."""
-        self.H0.copy_(H0_local)
-        src, dst = self.buf
-        src[:self.n_local].copy_(self.H0)
-        for _ in range(iterations):
-            self._step(src, dst, alpha)
-            src, dst = dst, src
-        return src[:self.n_local]
+        """K fused steps on this shard; returns this rank's rows of H_K ([n_local, F])."""
+        cur = []
+        for part in self.parts:
+            part["H0"].copy_(H0_local[:, part["col0"]:part["col0"] + part["F"]])
+            src, dst = part["buf"]
+            src[:self.n_local].copy_(part["H0"])
+            cur.append([src, dst])
+        if iterations > 0:
+            for part, (src, _) in zip(self.parts, cur):
+                self._start_exchange(part, src)
+        for k in range(iterations):
+            for part, pair in zip(self.parts, cur):
+                src, dst = pair
+                self._compute(part, src, dst, alpha)
+                pair[0], pair[1] = dst, src
+                if k + 1 < iterations:      # this half's next exchange overlaps the other half's compute
+                    self._start_exchange(part, pair[0])
+        if len(self.parts) == 1:
+            return cur[0][0][:self.n_local]
+        return torch.cat([pair[0][:self.n_local] for pair in cur], dim=1)
 
     def propagate_host_timed(self, alpha, iterations, reps=3):
         """End-to-end: pinned host H0 shard -> device, K steps, result shard -> host."""

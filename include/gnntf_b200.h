@@ -144,6 +144,11 @@ int gnntf_spmm_plan_fill(const int32_t* row_ptr, int64_t n_rows, int32_t long_th
  * ---------------------------------------------------------------------------------------- */
 int gnntf_spmm_f32(const gnntf_csr_t* A, const float* B, int64_t ldb, float* C, int64_t ldc,
                    int64_t F, void* stream);
+/* C[row_map[i],:] += scale · (A·B)[i,:] — the second pass of a sharded step: the entries whose
+ * columns are halo rows are accumulated onto the result of the owned-column pass once the halo has
+ * arrived.  Rows are the CSR's own (row_map selects the output rows); B and C must not alias. */
+int gnntf_spmm_acc_f32(const gnntf_csr_t* A, const float* B, int64_t ldb, float* C, int64_t ldc,
+                       int64_t F, double scale, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * (c) one PPRIteration, fused                                          filter.py:19-22

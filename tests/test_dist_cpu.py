@@ -98,3 +98,31 @@ def test_partition_is_nnz_balanced():
     loads = [int(row_ptr[b[i + 1]] - row_ptr[b[i]]) for i in range(4)]
     assert max(loads) <= 1000 + 10 and sum(loads) == 1999       # the hub row is a shard of its own
     assert gdist.partition_bounds(row_ptr, 1) == [0, 1000]
+
+
+def test_split_by_column_preserves_entries_and_order():
+    sys.path.insert(0, os.path.join(ROOT, "gnn-tf_b200"))
+    from gnntf import dist as gdist
+    rng = np.random.default_rng(4)
+    n_local, n_halo = 50, 30
+    deg = rng.integers(0, 12, n_local)
+    deg[3] = 0
+    row_ptr = torch.zeros(n_local + 1, dtype=torch.int32)
+    row_ptr[1:] = torch.from_numpy(np.cumsum(deg)).to(torch.int32)
+    nnz = int(row_ptr[-1])
+    col = torch.from_numpy(rng.integers(0, n_local + n_halo, nnz)).to(torch.int32)
+    val = torch.from_numpy(rng.random(nnz).astype(np.float32))
+    (o_rp, o_col, o_val), (h_rp, h_col, h_val), rows = gdist.split_by_column(row_ptr, col, val, n_local)
+    assert int(o_rp[-1]) + int(h_rp[-1]) == nnz and o_rp.numel() == n_local + 1
+    assert bool((o_col < n_local).all()) and bool((h_col >= n_local).all())
+    hmap = {int(r): i for i, r in enumerate(rows.tolist())}
+    for r in range(n_local):
+        s, e = int(row_ptr[r]), int(row_ptr[r + 1])
+        c, v = col[s:e], val[s:e]
+        own = c < n_local
+        assert torch.equal(o_col[int(o_rp[r]):int(o_rp[r + 1])], c[own]) and torch.equal(o_val[int(o_rp[r]):int(o_rp[r + 1])], v[own])
+        if (~own).any():
+            i = hmap[r]
+            assert torch.equal(h_col[int(h_rp[i]):int(h_rp[i + 1])], c[~own]) and torch.equal(h_val[int(h_rp[i]):int(h_rp[i + 1])], v[~own])
+        else:
+            assert r not in hmap

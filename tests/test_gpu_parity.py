@@ -466,7 +466,7 @@ def test_sharded_propagator_emulated_ranks(world):
 
     def exchange(me, send_buf, halo_out):  # deliver every peer's packed rows for `me`
         pass
-    props = [gdist.ShardedPropagator(adj, A, F, r, world, plan=plans[r], exchange=exchange) for r in range(world)]
+    props = [gdist.ShardedPropagator(adj, A, F, r, world, plan=plans[r], exchange=exchange, halves=1) for r in range(world)]
     # lock-step emulation of the K steps: pack on every rank, route, then compute on every rank
     L, nat = gnntf._native.lib(), gnntf._native
     bufs = [(p.buf[0], p.buf[1]) for p in props]
@@ -491,3 +491,46 @@ def test_sharded_propagator_emulated_ranks(world):
     got = torch.cat([src[:p.n_local] for p, (src, dst) in zip(props, bufs)])
     oracle.assert_close(_np(got), _np(expect), what="sharded vs single-GPU propagation")
     assert props[0].launches_per_propagation(K) >= 2 * K
+    assert props[0].owned.nnz + props[0].halo_part.nnz == props[0].nnz_local and props[0].halo_part.nnz > 0
+
+
+def test_sharded_propagator_column_halves_world1_matches():
+    """The two-half software pipeline (used when world > 1) on one rank: same result as one chain."""
+    gnntf = _gnntf()
+    from gnntf import dist as gdist
+    n, edges = synthetic.shaped_edges("arxiv", seed=0, device="cuda", scale=0.1)
+    adj = gnntf.edges2adj(edges, None, n)
+    A = adj.normalized("symmetric")
+    H0 = synthetic.features(n, 100, 1, "cuda")
+    expect = gnntf.appnp_propagate(A, H0, 0.1, 10)
+    for halves in (1, 2):
+        prop = gdist.ShardedPropagator(adj, A, 100, 0, 1, halves=halves)
+        assert len(prop.parts) == halves and sum(p["F"] for p in prop.parts) == 100
+        got = prop.propagate(H0, 0.1, 10)
+        oracle.assert_close(_np(got), _np(expect), what=f"halves={halves}")
+
+
+@pytest.mark.parametrize("F", [40, 100, 128])
+def test_spmm_short_rows_mapping_and_accumulate(F):
+    """Very short rows (the shape of the halo-column pass of a shard) and gnntf_spmm_acc_f32
+    (C += scale * A.B), the second pass of a sharded step."""
+    import ctypes
+    gnntf = _gnntf()
+    nat = gnntf._native
+    n, e = 5000, 7000
+    edges, w = _random_edges(n, e, seed=F)
+    adj = gnntf.edges2adj(edges, w, n)
+    assert adj.csr.nnz < 12 * n
+    A = adj.normalized("symmetric")
+    rng = np.random.default_rng(3)
+    H = rng.standard_normal((n, F)).astype(np.float32)
+    C0 = rng.standard_normal((n, F)).astype(np.float32)
+    idx, val, _ = oracle.graph2adj_arrays(edges, w, n)
+    _, nv, _ = oracle.get_adjacency(idx, val, n)
+    P = oracle.spmm_coo(idx, nv, H)
+    oracle.assert_close(_np(gnntf.sparse_dense_matmul(A, torch.from_numpy(H).cuda())), P, what="short rows SpMM")
+    C = torch.from_numpy(C0).cuda()
+    s = A.struct(F)
+    nat.check(nat.lib().gnntf_spmm_acc_f32(ctypes.byref(s), nat.ptr(torch.from_numpy(H).cuda()), F, nat.ptr(C), F, F, 0.9,
+                                           nat.stream_ptr()))
+    oracle.assert_close(_np(C), C0 + np.float32(0.9) * P, what="accumulate pass")
