@@ -246,11 +246,19 @@ def gpu_arm(args):
 
     if world > 1:
         from gnntf import dist as gdist
-        prop = gdist.ShardedPropagator(adj, A, F_run, rank, world, halves=args.halves or None)
-        log(f"[shard {rank}] rows {prop.lo}:{prop.hi} nnz {prop.nnz_local} halo rows {prop.n_halo} owned-column entries {prop.owned.nnz} halo-column entries {prop.halo_part.nnz} (rows {prop.halo_part.n}) parts {[p['F'] for p in prop.parts]}")
-        H0_local = H0[prop.lo:prop.hi].contiguous()
+        R, C = (int(x) for x in args.grid.split("x")) if args.grid else gdist.choose_grid(world, F_run)
+        grid = gdist.Grid2D(rank, world, R, C)
+        c0, c1 = gdist.column_range(F_run, C, grid.c)
+        prop = gdist.ShardedPropagator(adj, A, c1 - c0, grid.r, R, group=grid.row_group, halves=args.halves or None,
+                                       push=not args.nccl_exchange)
+        log(f"[rank {rank} = row group {grid.r}/{R}, column group {grid.c}/{C}] rows {prop.lo}:{prop.hi} cols {c0}:{c1} "
+            f"nnz {prop.nnz_local} halo rows {prop.n_halo} owned-column entries {prop.owned.nnz} "
+            f"halo-column entries {prop.halo_part.nnz} (rows {prop.halo_part.n})")
+        H0_local = H0[prop.lo:prop.hi, c0:c1].contiguous()
         run = lambda: prop.propagate(H0_local, ALPHA, K_ITER)  # noqa: E731
         launches_per_step = prop.launches_per_propagation(K_ITER)
+        sharding = (f"{R} row groups (contiguous node ranges balanced by nnz; halo rows by NCCL all-to-all inside a column "
+                    f"group) x {C} feature-column groups (no communication)")
         del H0
     else:
         out = torch.empty_like(H0)
@@ -298,7 +306,7 @@ def gpu_arm(args):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic", "config": dict(config_dict(args, n, E, nnz, F), padded_features=F_run,
-                           sharding=(f"contiguous node ranges balanced by nnz over {world} GPUs; halo rows by NCCL all-to-all" if world > 1 else "none")),
+                           sharding=(sharding if world > 1 else "none")),
             "propagation_ms": {"mean": ms_per_step, "min": float(per_step_ms.min().item()),
                                "median": float(per_step_ms.median().item())},
             "clocks": clocks, "gpu_launches": launches_per_step * args.steps,
@@ -385,6 +393,8 @@ def main():
     ap.add_argument("--features", type=int, default=0, help="feature width (default: the shape's)")
     ap.add_argument("--scale", type=float, default=1.0, help="shrink the graph (tests only; 1.0 = BASELINE size)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--grid", default="", help="multi-GPU layout ROWSxCOLS (default: gnntf.dist.choose_grid)")
+    ap.add_argument("--nccl-exchange", action="store_true", help="multi-GPU: halo rows by NCCL all-to-all instead of the fused peer-memory push")
     ap.add_argument("--halves", type=int, default=0, help="multi-GPU: feature-column chains to pipeline (0 = default)")
     args = ap.parse_args()
     if args.impl == "reference":

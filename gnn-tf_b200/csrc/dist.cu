@@ -4,6 +4,8 @@
 // (gnntf/core/gnn/architectures/filter.py:19-22) is otherwise unchanged: the local CSR simply
 // addresses [owned rows | halo rows].
 #include <algorithm>
+#include <cstdlib>
+#include <cstring>
 
 #include "common.cuh"
 
@@ -19,6 +21,28 @@ __global__ void halo_pack_kernel(const float* __restrict__ H, int64_t ld, const 
     for (int64_t i = warp; i < n_send; i += nwarps) {
         const float* src = H + (int64_t)__ldg(send_idx + i) * ld;
         float* dst = out + i * ldo;
+        for (int f = lane * VEC; f < F; f += 32 * VEC) Vec<VEC>::gather(src + f).store(dst + f);
+    }
+}
+
+// Fused pack + send: one warp per row; the destination is a peer GPU's halo buffer (NVLink stores).
+template <int VEC>
+__global__ void halo_push_kernel(const float* __restrict__ H, int64_t ld, const int32_t* __restrict__ send_idx,
+                                 const int64_t* __restrict__ send_off, float* const* __restrict__ peer_base,
+                                 const int64_t* __restrict__ peer_row0, int n_peers, int64_t n_send,
+                                 int64_t rotate, int64_t ldo, int F) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t k = warp; k < n_send; k += nwarps) {
+        // every rank starts with a different destination, so at any moment each receiver is the
+        // target of (about) one sender instead of all of them
+        int64_t i = k + rotate;
+        if (i >= n_send) i -= n_send;
+        int d = 0;
+        while (d + 1 < n_peers && i >= send_off[d + 1]) ++d;   // n_peers <= 8: linear scan
+        const float* src = H + (int64_t)__ldg(send_idx + i) * ld;
+        float* dst = peer_base[d] + (peer_row0[d] + (i - send_off[d])) * ldo;
         for (int f = lane * VEC; f < F; f += 32 * VEC) Vec<VEC>::gather(src + f).store(dst + f);
     }
 }
@@ -40,5 +64,65 @@ extern "C" int gnntf_halo_pack_f32(const float* H, int64_t ld, const int32_t* se
     else
         halo_pack_kernel<1><<<grid, 256, 0, (cudaStream_t)stream>>>(H, ld, send_idx, n_send, out, ldo, (int)F);
     GNNTF_LAUNCH_CHECK();
+    return GNNTF_OK;
+}
+
+extern "C" int gnntf_halo_push_f32(const float* H, int64_t ld, const int32_t* send_idx, const int64_t* send_off,
+                                   float* const* peer_base, const int64_t* peer_row0, int n_peers,
+                                   int64_t n_send, int64_t rotate, int64_t ldo, int64_t F, void* stream) {
+    if (n_send < 0 || F < 0 || F > 0x7fffffff || ld < F || ldo < F || n_peers < 1 || n_peers > 64) return GNNTF_E_SIZE;
+    if (rotate < 0 || (n_send > 0 && rotate >= n_send)) return GNNTF_E_SIZE;
+    if (n_send == 0 || F == 0) return GNNTF_OK;
+    if (H == nullptr || send_idx == nullptr || send_off == nullptr || peer_base == nullptr || peer_row0 == nullptr)
+        return GNNTF_E_NULL;
+    // The push overlaps the owned-column SpMM pass: a small grid leaves the SMs to that kernel
+    // (NVLink needs far fewer warps in flight than HBM does).  GNNTF_PUSH_CTAS overrides.
+    static const int max_ctas = [] { const char* e = getenv("GNNTF_PUSH_CTAS"); return e ? std::max(1, atoi(e)) : kNumSMs; }();
+    const int grid = (int)std::min<int64_t>(ceil_div(n_send, 8), (int64_t)max_ctas);
+    const bool v4 = (F % 4 == 0) && (ld % 4 == 0) && (ldo % 4 == 0) && (reinterpret_cast<uintptr_t>(H) & 15u) == 0;
+    if (v4)
+        halo_push_kernel<4><<<grid, 256, 0, (cudaStream_t)stream>>>(H, ld, send_idx, send_off, peer_base, peer_row0,
+                                                                     n_peers, n_send, rotate, ldo, (int)F);
+    else
+        halo_push_kernel<1><<<grid, 256, 0, (cudaStream_t)stream>>>(H, ld, send_idx, send_off, peer_base, peer_row0,
+                                                                     n_peers, n_send, rotate, ldo, (int)F);
+    GNNTF_LAUNCH_CHECK();
+    return GNNTF_OK;
+}
+
+static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+
+extern "C" int gnntf_ipc_alloc(size_t bytes, void** dev_ptr, unsigned char handle[64]) {
+    if (dev_ptr == nullptr || handle == nullptr) return GNNTF_E_NULL;
+    if (bytes == 0) return GNNTF_E_SIZE;
+    GNNTF_CUDA_TRY(cudaMalloc(dev_ptr, bytes));
+    cudaIpcMemHandle_t h;
+    cudaError_t e = cudaIpcGetMemHandle(&h, *dev_ptr);
+    if (e != cudaSuccess) {
+        cudaFree(*dev_ptr);
+        *dev_ptr = nullptr;
+        return (int)e;
+    }
+    memcpy(handle, &h, 64);
+    return GNNTF_OK;
+}
+
+extern "C" int gnntf_ipc_open(const unsigned char handle[64], void** dev_ptr) {
+    if (dev_ptr == nullptr || handle == nullptr) return GNNTF_E_NULL;
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, 64);
+    GNNTF_CUDA_TRY(cudaIpcOpenMemHandle(dev_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return GNNTF_OK;
+}
+
+extern "C" int gnntf_ipc_close(void* dev_ptr) {
+    if (dev_ptr == nullptr) return GNNTF_OK;
+    GNNTF_CUDA_TRY(cudaIpcCloseMemHandle(dev_ptr));
+    return GNNTF_OK;
+}
+
+extern "C" int gnntf_ipc_free(void* dev_ptr) {
+    if (dev_ptr == nullptr) return GNNTF_OK;
+    GNNTF_CUDA_TRY(cudaFree(dev_ptr));
     return GNNTF_OK;
 }

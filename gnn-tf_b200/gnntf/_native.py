@@ -24,7 +24,7 @@ SYMBOLS = [
     "gnntf_normalize_f32", "gnntf_spmm_plan_count", "gnntf_spmm_plan_fill", "gnntf_spmm_f32", "gnntf_spmm_acc_f32",
     "gnntf_appnp_step_f32", "gnntf_appnp_propagate_f32", "gnntf_appnp_propagate_multi_f32",
     "gnntf_appnp_propagate_bwd_f32", "gnntf_appnp_propagate_host_f32",
-    "gnntf_halo_pack_f32",
+    "gnntf_halo_pack_f32", "gnntf_halo_push_f32", "gnntf_ipc_alloc", "gnntf_ipc_open", "gnntf_ipc_close", "gnntf_ipc_free",
 ]
 
 
@@ -83,6 +83,12 @@ def lib():
     L.gnntf_appnp_propagate_host_f32.argtypes = [POINTER(CsrStruct), c_void_p, c_void_p, c_void_p, c_void_p,
                                                  c_void_p, c_int64, c_int64, c_double, c_int, c_void_p]
     L.gnntf_halo_pack_f32.argtypes = [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_int64, c_void_p]
+    L.gnntf_halo_push_f32.argtypes = [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int64, c_int64,
+                                      c_int64, c_int64, c_void_p]
+    L.gnntf_ipc_alloc.argtypes = [c_size_t, POINTER(c_void_p), c_void_p]
+    L.gnntf_ipc_open.argtypes = [c_void_p, POINTER(c_void_p)]
+    L.gnntf_ipc_close.argtypes = [c_void_p]
+    L.gnntf_ipc_free.argtypes = [c_void_p]
     for name in SYMBOLS:
         fn = getattr(L, name)
         if name not in ("gnntf_status_str",):

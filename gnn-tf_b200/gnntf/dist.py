@@ -27,6 +27,39 @@ import torch
 import torch.distributed as dist
 
 
+def choose_grid(world, F):
+    """(row_groups, column_groups) for ``world`` GPUs.  Feature columns propagate independently
+    through H <- (1-a)·Â·H + a·H0, so splitting them needs NO communication, and it shrinks every
+    rank's halo bytes by the column factor; but narrower feature rows gather less efficiently and
+    every column group re-reads the CSR.  Measured on the products shape: two
+    column groups win from 2 GPUs up as long as each keeps >= 48 columns."""
+    cols = 2 if (world % 2 == 0 and F >= 96) else 1
+    return world // cols, cols
+
+
+def column_range(F, col_groups, c):
+    """Columns [c0, c1) of column group c: equal shares rounded up to a multiple of 4 floats."""
+    share = ((F + col_groups - 1) // col_groups + 3) // 4 * 4
+    c0 = min(F, c * share)
+    return c0, min(F, c0 + share)
+
+
+class Grid2D:
+    """rank -> (row group r of R, column group c of C) with one process group per column group
+    (its R ranks exchange halo rows among themselves; column groups never talk)."""
+
+    def __init__(self, rank, world, rows, cols):
+        assert rows * cols == world
+        self.rank, self.world, self.R, self.C = rank, world, rows, cols
+        self.r, self.c = rank // cols, rank % cols
+        self.row_group = None
+        if world > 1:
+            for c in range(cols):  # every rank creates every group, in the same order
+                g = dist.new_group(ranks=[r * cols + c for r in range(rows)])
+                if c == self.c:
+                    self.row_group = g
+
+
 def partition_bounds(row_ptr, world):
     """Contiguous node ranges with (nearly) equal nnz: bounds[k] = first row whose row_ptr reaches
     k/world of nnz.  Identical on every rank (pure function of row_ptr)."""
@@ -166,6 +199,33 @@ def p_world_gt1(world):
     return world > 1 and torch.cuda.is_available()
 
 
+class _SharedMatrix:
+    """fp32 [rows, cols] device matrix allocated through gnntf_ipc_alloc so that peers can map it
+    (CUDA IPC) and store halo rows into it directly; exposed to torch without a copy."""
+
+    def __init__(self, rows, cols, device):
+        from . import _native as nat
+        self.nat, self.rows, self.cols = nat, int(rows), int(cols)
+        ptr = ctypes.c_void_p()
+        self.handle = (ctypes.c_ubyte * 64)()
+        with torch.cuda.device(device):
+            nat.check(nat.lib().gnntf_ipc_alloc(max(16, self.rows * self.cols * 4), ctypes.byref(ptr), self.handle), "ipc_alloc")
+        self.ptr = ptr.value
+        self.__cuda_array_interface__ = {"shape": (self.rows, self.cols), "typestr": "<f4", "data": (self.ptr, False),
+                                         "version": 2, "strides": None}
+        self.tensor = torch.as_tensor(self, device=device)
+        self.tensor.zero_()
+
+    def handle_bytes(self):
+        return bytes(self.handle)
+
+    def __del__(self):
+        try:
+            self.nat.lib().gnntf_ipc_free(ctypes.c_void_p(self.ptr))
+        except Exception:
+            pass
+
+
 class _EventWork:
     """``work.wait()`` for the single-process emulation hook: the compute stream waits for an event."""
 
@@ -185,7 +245,7 @@ class ShardedPropagator:
     is in flight while the other half computes step k.  Costs a second pass over the CSR and
     narrower gathers (~1.2x compute), hides most of the exchange."""
 
-    def __init__(self, adj, A, F, rank, world, group=None, plan=None, exchange=None, halves=None):
+    def __init__(self, adj, A, F, rank, world, group=None, plan=None, exchange=None, halves=None, push=True):
         from . import _native as nat
         from .sparse import CsrStructure
         self.nat = nat
@@ -208,15 +268,60 @@ class ShardedPropagator:
         first = ((self.F + halves - 1) // halves + 3) // 4 * 4 if halves > 1 else self.F
         widths = [first, self.F - first] if halves > 1 and self.F - first > 0 else [self.F]
         n_ext, n_send = self.n_local + self.n_halo, int(sum(p.send_counts))
-        self.parts, col0 = [], 0
+        self.push = bool(push) and p.world > 1 and exchange is None
+        self.parts, col0, self._shared = [], 0, []
         for w in widths:
-            self.parts.append(dict(F=w, col0=col0,
-                                   buf=[torch.zeros((n_ext, w), dtype=torch.float32, device=dev) for _ in range(2)],
+            if self.push:
+                mats = [_SharedMatrix(n_ext, w, dev) for _ in range(2)]
+                self._shared.append(mats)
+                bufs = [m.tensor for m in mats]
+            else:
+                bufs = [torch.zeros((n_ext, w), dtype=torch.float32, device=dev) for _ in range(2)]
+            self.parts.append(dict(F=w, col0=col0, buf=bufs,
                                    send=torch.empty((n_send, w), dtype=torch.float32, device=dev),
                                    H0=torch.empty((self.n_local, w), dtype=torch.float32, device=dev), work=None))
             col0 += w
+        if self.push:
+            self._map_peers()
         # single-part aliases (tests and the emulation hook address them directly)
         self.buf, self.send_buf, self.H0 = self.parts[0]["buf"], self.parts[0]["send"], self.parts[0]["H0"]
+
+    def _map_peers(self):
+        """Exchange IPC handles and halo layouts inside the row group and build, per part and per
+        ping-pong buffer, the device tables gnntf_halo_push_f32 needs."""
+        nat, L, p = self.nat, self.nat.lib(), self.plan
+        dev = p.row_ptr.device
+        mine = dict(handles=[[m.handle_bytes() for m in mats] for mats in self._shared],
+                    recv_counts=list(p.recv_counts), n_local=self.n_local)
+        everyone = [None] * p.world
+        dist.all_gather_object(everyone, mine, group=self.group)
+        send_off = [0]
+        for c in p.send_counts:
+            send_off.append(send_off[-1] + int(c))
+        self._send_off = torch.tensor(send_off, dtype=torch.int64, device=dev)
+        nxt = send_off[(p.rank + 1) % p.world]
+        self._rotate = int(nxt) if nxt < send_off[-1] else 0   # start with the next rank's rows
+        # my rows land in peer q's halo region after the rows of lower-ranked owners
+        row0 = [int(everyone[q]["n_local"]) + int(sum(everyone[q]["recv_counts"][:p.rank])) for q in range(p.world)]
+        self._peer_row0 = torch.tensor(row0, dtype=torch.int64, device=dev)
+        self._peer_ptrs, self._opened = [], []
+        for pi in range(len(self.parts)):
+            per_buf = []
+            for bi in range(2):
+                ptrs = []
+                for q in range(p.world):
+                    if q == p.rank or p.send_counts[q] == 0:
+                        ptrs.append(0)
+                        continue
+                    h = (ctypes.c_ubyte * 64).from_buffer_copy(everyone[q]["handles"][pi][bi])
+                    out = ctypes.c_void_p()
+                    nat.check(L.gnntf_ipc_open(h, ctypes.byref(out)), "ipc_open")
+                    self._opened.append(out.value)
+                    ptrs.append(out.value)
+                per_buf.append(torch.tensor(ptrs, dtype=torch.int64, device=dev))
+            self._peer_ptrs.append(per_buf)
+        self._flag = torch.zeros(1, dtype=torch.float32, device=dev)
+        dist.barrier(group=self.group)
 
     def launches_per_propagation(self, K):
         per_step = 1 if self.plan.world > 1 else 0  # pack
@@ -238,6 +343,18 @@ class ShardedPropagator:
         ready.record()                                   # src complete on the compute stream
         with torch.cuda.stream(self.comm_stream):
             self.comm_stream.wait_event(ready)
+            if self.push:
+                # fused pack + send: rows go straight into the peers' halo regions of the SAME
+                # ping-pong buffer; a one-element all-reduce is the cross-rank completion barrier
+                pi = self.parts.index(part)
+                bi = 0 if src.data_ptr() == part["buf"][0].data_ptr() else 1
+                n_send = int(p.send_idx.numel())
+                if n_send > 0:
+                    nat.check(L.gnntf_halo_push_f32(nat.ptr(src), F, nat.ptr(p.send_idx), nat.ptr(self._send_off),
+                                                    nat.ptr(self._peer_ptrs[pi][bi]), nat.ptr(self._peer_row0), p.world,
+                                                    n_send, self._rotate, F, F, nat.stream_ptr()), "halo_push")
+                part["work"] = dist.all_reduce(self._flag, group=self.group, async_op=True)
+                return
             if part["send"].shape[0] > 0:
                 nat.check(L.gnntf_halo_pack_f32(nat.ptr(src), F, nat.ptr(p.send_idx), part["send"].shape[0],
                                                 nat.ptr(part["send"]), F, F, nat.stream_ptr()), "halo_pack")
@@ -305,17 +422,18 @@ class ShardedPropagator:
             host_out.copy_(out, non_blocking=True)
             torch.cuda.synchronize()
         once()
-        if self.plan.world > 1:
-            dist.barrier(group=self.group)
+        multi = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+        if multi:
+            dist.barrier()                       # timing spans ALL ranks (every column group)
         t0 = time.perf_counter()
         for _ in range(reps):
             once()
-        if self.plan.world > 1:
-            dist.barrier(group=self.group)
+        if multi:
+            dist.barrier()
         sec = (time.perf_counter() - t0) / reps
         t = torch.tensor([sec], dtype=torch.float64, device=self.H0.device)
         nbytes = torch.tensor([float(host_in.numel() * 4)], dtype=torch.float64, device=self.H0.device)
-        if self.plan.world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.group)
-            dist.all_reduce(nbytes, op=dist.ReduceOp.SUM, group=self.group)
+        if multi:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dist.all_reduce(nbytes, op=dist.ReduceOp.SUM)
         return {"seconds": float(t.item()), "h2d": int(nbytes.item()), "d2h": int(nbytes.item())}

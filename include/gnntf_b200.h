@@ -194,6 +194,26 @@ int gnntf_appnp_propagate_host_f32(const gnntf_csr_t* A, const float* H0_host, f
  * ---------------------------------------------------------------------------------------- */
 int gnntf_halo_pack_f32(const float* H, int64_t ld, const int32_t* send_idx, int64_t n_send,
                         float* out, int64_t ldo, int64_t F, void* stream);
+/* Fused pack + send over NVLink peer memory: row send_idx[i] of H, for i in
+ * [send_off[d], send_off[d+1]), is stored straight into peer d's halo buffer
+ *   peer_base[d] + (peer_row0[d] + i - send_off[d]) * ldo
+ * (peer_base: device array of `n_peers` pointers mapped with CUDA IPC; entries whose send range is
+ * empty may be NULL).  send_off / peer_base / peer_row0 are DEVICE arrays.  The list is walked
+ * starting at row `rotate` (wrapping), so ranks can start with different destinations and avoid
+ * all hitting the same receiver at once.  The caller follows it
+ * with a cross-rank barrier (a one-element NCCL all-reduce) before reading its own halo rows. */
+int gnntf_halo_push_f32(const float* H, int64_t ld, const int32_t* send_idx, const int64_t* send_off,
+                        float* const* peer_base, const int64_t* peer_row0, int n_peers,
+                        int64_t n_send, int64_t rotate, int64_t ldo, int64_t F, void* stream);
+
+/* Peer-memory plumbing for gnntf_halo_push_f32 (the only entry points that allocate; used once at
+ * shard set-up).  gnntf_ipc_alloc: cudaMalloc + cudaIpcGetMemHandle (handle = 64 bytes, shipped to
+ * the peers through the host's own channel, e.g. torch.distributed.all_gather_object).
+ * gnntf_ipc_open: map a peer's allocation into this process (peer access enabled lazily). */
+int gnntf_ipc_alloc(size_t bytes, void** dev_ptr, unsigned char handle[64]);
+int gnntf_ipc_open(const unsigned char handle[64], void** dev_ptr);
+int gnntf_ipc_close(void* dev_ptr);
+int gnntf_ipc_free(void* dev_ptr);
 
 #ifdef __cplusplus
 }
