@@ -29,11 +29,12 @@ import torch.distributed as dist
 
 def choose_grid(world, F):
     """(row_groups, column_groups) for ``world`` GPUs.  Feature columns propagate independently
-    through H <- (1-a)·Â·H + a·H0, so splitting them needs NO communication, and it shrinks every
+    through H <- (1-a)·Â·H + a·H0, so splitting them needs NO communication and shrinks every
     rank's halo bytes by the column factor; but narrower feature rows gather less efficiently and
-    every column group re-reads the CSR.  Measured on the products shape: two
-    column groups win from 2 GPUs up as long as each keeps >= 48 columns."""
-    cols = 2 if (world % 2 == 0 and F >= 96) else 1
+    every column group re-reads the whole CSR of its row group.  Measured on the products shape,
+    F=100: rows only up to 4 GPUs (2x1 33.1 ms vs 1x2 35.6; 4x1 20.2 vs 2x2 21.7),
+    two column groups at 8 (4x2 16.4 ms vs 8x1 17.2)."""
+    cols = 2 if (world >= 8 and world % 2 == 0 and F >= 96) else 1
     return world // cols, cols
 
 
