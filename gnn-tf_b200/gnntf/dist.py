@@ -283,7 +283,16 @@ class ShardedPropagator:
                                    H0=torch.empty((self.n_local, w), dtype=torch.float32, device=dev), work=None))
             col0 += w
         if self.push:
-            self._map_peers()
+            # every rank of the row group must take the same path: agree on whether IPC mapping worked
+            try:
+                self._map_peers()
+                ok = 1.0
+            except Exception as err:  # e.g. peers without CUDA IPC / peer access
+                ok, self._map_error = 0.0, err
+            flag = torch.tensor([ok], dtype=torch.float32, device=dev)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.group)
+            if flag.item() < 1.0:
+                self.push = False  # the shared buffers are ordinary device memory for the NCCL path
         # single-part aliases (tests and the emulation hook address them directly)
         self.buf, self.send_buf, self.H0 = self.parts[0]["buf"], self.parts[0]["send"], self.parts[0]["H0"]
 
@@ -322,7 +331,6 @@ class ShardedPropagator:
                 per_buf.append(torch.tensor(ptrs, dtype=torch.int64, device=dev))
             self._peer_ptrs.append(per_buf)
         self._flag = torch.zeros(1, dtype=torch.float32, device=dev)
-        dist.barrier(group=self.group)
 
     def launches_per_propagation(self, K):
         per_step = 1 if self.plan.world > 1 else 0  # pack
