@@ -264,7 +264,7 @@ def gpu_arm(args):
         out = torch.empty_like(H0)
         scratch = torch.empty_like(H0)
         run = lambda: ops.propagate_raw(A, H0, ALPHA, K_ITER, out=out, scratch=scratch)  # noqa: E731
-        launches_per_step = K_ITER * (3 if adj.csr.n_long > 0 else 1)
+        launches_per_step = K_ITER * (2 if adj.csr.n_long > 0 else 1)  # row kernel (pieces ride in its grid) + long-row reduce
     flush = None
     if step_bytes(n, nnz, F) <= 3 * 126e6:
         flush = torch.empty(64 * 1024 * 1024, dtype=torch.float32, device=dev)

@@ -93,6 +93,105 @@ __device__ __forceinline__ void st_once4(float* p, float4 v, uint64_t pol) {
 
 
 // ---------------------------------------------------------------------------------------------
+// Long rows, phase 1: one warp per 256-entry piece.  The 32/GROUP lane groups take the piece's
+// entries round-robin and are combined with xor-shuffles in a fixed pattern; the result goes to
+// partials[piece, ldp] (ldp = round_up(F,4)).  Runs inside the row kernel's grid (the first
+// `piece_ctas` CTAs), so the pieces overlap the ordinary rows instead of being a second launch.
+// ---------------------------------------------------------------------------------------------
+struct PieceArgs {
+    const int* chunk_row;
+    const int* chunk_begin;
+    int n_chunks;
+    int chunk;
+    float* partials;
+    int ldp;
+};
+
+template <int VEC, int NSLOT, int GROUP, int UNROLL>
+__device__ __forceinline__ void process_piece(const int* __restrict__ row_ptr, const int* __restrict__ col_idx,
+                                              const float* __restrict__ val, const float* __restrict__ B,
+                                              int64_t ldb, const int* __restrict__ chunk_row,
+                                              const int* __restrict__ chunk_begin, int piece, int chunk,
+                                              float* __restrict__ partials, int ldp, int F, int f_base) {
+    constexpr int NGROUPS = 32 / GROUP;
+    const int lane = threadIdx.x & 31;
+    const int g = lane / GROUP;
+    const int gl = lane % GROUP;
+    const int row = __ldg(chunk_row + piece);
+    const int begin = __ldg(chunk_begin + piece);
+    const int end = min(begin + chunk, __ldg(row_ptr + row + 1));
+
+    int fo[NSLOT];
+    bool fok[NSLOT];
+#pragma unroll
+    for (int s = 0; s < NSLOT; ++s) {
+        fo[s] = f_base + (s * GROUP + gl) * VEC;
+        fok[s] = fo[s] < F;
+    }
+    Vec<VEC> acc[NSLOT];
+#pragma unroll
+    for (int s = 0; s < NSLOT; ++s)
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) acc[s].v[i] = 0.0f;
+
+    // 32 entries per outer step: lane l holds entry base+l; group g consumes entries with
+    // (index % NGROUPS) == g.
+    for (int base = begin; base < end; base += 32) {
+        int c = 0;
+        float v = 0.0f;
+        if (base + lane < end) {
+            c = ld_stream(col_idx + base + lane);
+            v = ld_stream(val + base + lane);
+        }
+        const int cnt = min(32, end - base);
+        for (int j = 0; j < cnt; j += NGROUPS * UNROLL) {
+            int cj[UNROLL];
+            float vj[UNROLL];
+#pragma unroll
+            for (int u = 0; u < UNROLL; ++u) {
+                const int src = j + u * NGROUPS + g;
+                cj[u] = __shfl_sync(0xffffffffu, c, src & 31);
+                vj[u] = __shfl_sync(0xffffffffu, v, src & 31);
+                if (src >= cnt) vj[u] = 0.0f, cj[u] = -1;
+            }
+            Vec<VEC> x[UNROLL][NSLOT];
+#pragma unroll
+            for (int u = 0; u < UNROLL; ++u) {
+                const float* src = B + (int64_t)cj[u] * ldb;
+#pragma unroll
+                for (int s = 0; s < NSLOT; ++s) {
+                    if (cj[u] >= 0 && fok[s]) {
+                        x[u][s] = Vec<VEC>::gather(src + fo[s]);
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < VEC; ++i) x[u][s].v[i] = 0.0f;
+                    }
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < UNROLL; ++u)
+#pragma unroll
+                for (int s = 0; s < NSLOT; ++s)
+#pragma unroll
+                    for (int i = 0; i < VEC; ++i) acc[s].v[i] = fmaf(vj[u], x[u][s].v[i], acc[s].v[i]);
+        }
+    }
+    if (NGROUPS > 1) {
+#pragma unroll
+        for (int o = GROUP; o < 32; o <<= 1)
+#pragma unroll
+            for (int s = 0; s < NSLOT; ++s)
+#pragma unroll
+                for (int i = 0; i < VEC; ++i) acc[s].v[i] += __shfl_xor_sync(0xffffffffu, acc[s].v[i], o);
+    }
+    if (g == 0) {
+#pragma unroll
+        for (int s = 0; s < NSLOT; ++s)
+            if (fok[s]) acc[s].store(partials + (int64_t)piece * ldp + fo[s]);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // Main kernel: GROUP lanes per sparse row; rows with deg > long_threshold are left to the piece
 // path.  A CTA walks blocks_per_cta consecutive row blocks (fewer, longer-lived CTAs: the per-row
 // version launched 306 k CTAs on the products shape and ran at 47 % achieved occupancy);
@@ -116,15 +215,25 @@ __global__ void __launch_bounds__(THREADS, MINB)
 spmm_rows_kernel(const int* __restrict__ row_ptr, const int* __restrict__ col_idx,
                  const float* __restrict__ val, const int* __restrict__ row_map,
                  const float* __restrict__ B, int64_t ldb, int n_rows, int long_threshold,
-                 int blocks_per_cta, Epilogue epi) {
-    static_assert(UNROLL % 2 == 0 && GROUP % 2 == 0, "entries are read back two at a time");
+                 int blocks_per_cta, int piece_ctas, PieceArgs pieces, Epilogue epi) {
+    static_assert(UNROLL % 2 == 0 && GROUP % UNROLL == 0, "entries are read back two at a time, whole batches");
+    if ((int)blockIdx.x < piece_ctas) {  // CTA-uniform: this CTA works on pieces of split rows
+        const int piece = blockIdx.x * (THREADS / 32) + (threadIdx.x >> 5);
+        if (piece < pieces.n_chunks)
+            process_piece<VEC, NSLOT, GROUP, (NSLOT >= 4) ? 2 : 4>(row_ptr, col_idx, val, B, ldb, pieces.chunk_row,
+                                                                  pieces.chunk_begin, piece, pieces.chunk,
+                                                                  pieces.partials, pieces.ldp, epi.F,
+                                                                  blockIdx.y * (GROUP * NSLOT * VEC));
+        return;
+    }
+    const int row_cta = blockIdx.x - piece_ctas;
     constexpr int ROWS_PER_WARP = 32 / GROUP;
     constexpr int WARPS = THREADS / 32;
     constexpr int ROWS_PER_BLOCK = WARPS * ROWS_PER_WARP;
     // (col,val) pairs of the current 32 entries of this warp, broadcast through shared memory:
     // one LDS.128 delivers two entries to every lane (0.5 L1 wavefronts per entry; the shuffle
     // pair it replaces cost 2 wavefronts and was a third of the L1 data-pipe traffic, profiles/r1/02)
-    __shared__ __align__(16) int2 cv_smem[WARPS][32 + UNROLL];
+    __shared__ __align__(16) int2 cv_smem[WARPS][32];
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     const int g = lane / GROUP;
@@ -145,10 +254,9 @@ spmm_rows_kernel(const int* __restrict__ row_ptr, const int* __restrict__ col_id
         fok[s] = fo[s] < F;  // VEC == 4 implies F % 4 == 0, so the whole slot is in range
         Bl[s] = B + (fok[s] ? fo[s] : 0);
     }
-    if (lane < UNROLL) cv[32 + lane] = make_int2(0, 0);  // padding read (never used) by ragged tails
 
     for (int it = 0; it < blocks_per_cta; ++it) {
-        const int64_t row = ((int64_t)blockIdx.x * blocks_per_cta + it) * ROWS_PER_BLOCK + warp * ROWS_PER_WARP + g;
+        const int64_t row = ((int64_t)row_cta * blocks_per_cta + it) * ROWS_PER_BLOCK + warp * ROWS_PER_WARP + g;
         if (row - g >= n_rows) break;  // warp-uniform: the whole warp is past the end
         int start = 0, deg = 0;
         bool mine = false;
@@ -158,12 +266,11 @@ spmm_rows_kernel(const int* __restrict__ row_ptr, const int* __restrict__ col_id
             mine = !(long_threshold > 0 && deg > long_threshold);
             if (!mine) deg = 0;
         }
-        int maxdeg = deg, mindeg = deg;
+        int maxdeg = deg;
         if (ROWS_PER_WARP > 1) {
 #pragma unroll
             for (int o = GROUP; o < 32; o <<= 1) {
                 maxdeg = max(maxdeg, __shfl_xor_sync(0xffffffffu, maxdeg, o));
-                mindeg = min(mindeg, __shfl_xor_sync(0xffffffffu, mindeg, o));
             }
         }
         Vec<VEC> acc[NSLOT];
@@ -172,20 +279,28 @@ spmm_rows_kernel(const int* __restrict__ row_ptr, const int* __restrict__ col_id
 #pragma unroll
             for (int i = 0; i < VEC; ++i) acc[s].v[i] = 0.0f;
 
+        // Slots past the end of a row are padded with (first column of the row, value 0): the
+        // batches then run predicate-free for every group of the warp, whatever its degree; the
+        // padded gathers re-read a row that is already in L1.  (0 * x leaves the sum unchanged for
+        // finite x; a non-finite feature row of the first neighbour already makes the true result
+        // non-finite.)
+        int c_pad = 0;
         for (int off = 0; off < maxdeg; off += GROUP) {
-            int c = 0;
+            int c = c_pad;
             float v = 0.0f;
             if (off + gl < deg) {
                 c = ld_once(col_idx + start + off + gl, pol);
                 v = ld_once(val + start + off + gl, pol);
             }
+            if (off == 0) {
+                c_pad = __shfl_sync(0xffffffffu, c, 0, GROUP);  // the row's first column (deg > 0)
+                if (gl >= deg) c = (deg > 0) ? c_pad : 0;
+            }
             __syncwarp();  // everyone is done reading the previous batch
             cv[lane] = make_int2(c, __float_as_int(v));
             __syncwarp();
             const int lim = min(GROUP, maxdeg - off);
-            const int full = min(GROUP, mindeg - off);  // entries every group of the warp still has
-            int j = 0;
-            for (; j + UNROLL <= full; j += UNROLL) {    // predicate-free batches
+            for (int j = 0; j < lim; j += UNROLL) {
                 int cj[UNROLL];
                 float vj[UNROLL];
 #pragma unroll
@@ -208,39 +323,12 @@ spmm_rows_kernel(const int* __restrict__ row_ptr, const int* __restrict__ col_id
 #pragma unroll
                             for (int i = 0; i < VEC; ++i) acc[s].v[i] = fmaf(vj[u], x[u][s].v[i], acc[s].v[i]);
             }
-            for (; j < lim; j += UNROLL) {               // ragged tail: per-entry predicates
-                int cj[UNROLL];
-                float vj[UNROLL];
+        }
+        if (deg == 0) {  // an empty (or split) row riding along in a warp: drop whatever the padding produced
 #pragma unroll
-                for (int u = 0; u < UNROLL; u += 2) {
-                    const int4 e = *reinterpret_cast<const int4*>(cv_group + j + u);
-                    cj[u] = e.x; vj[u] = __int_as_float(e.y);
-                    cj[u + 1] = e.z; vj[u + 1] = __int_as_float(e.w);
-                }
-                Vec<VEC> x[UNROLL][NSLOT];
+            for (int s = 0; s < NSLOT; ++s)
 #pragma unroll
-                for (int u = 0; u < UNROLL; ++u) {
-                    const bool live = (j + u < GROUP) && (off + j + u < deg);
-#pragma unroll
-                    for (int s = 0; s < NSLOT; ++s) {
-                        if (live && fok[s]) {
-                            x[u][s] = gather_row<VEC>(Bl[s], cj[u], pitch);
-                        } else {
-#pragma unroll
-                            for (int i = 0; i < VEC; ++i) x[u][s].v[i] = 0.0f;
-                        }
-                    }
-                }
-#pragma unroll
-                for (int u = 0; u < UNROLL; ++u) {
-                    const bool live = (j + u < GROUP) && (off + j + u < deg);
-#pragma unroll
-                    for (int s = 0; s < NSLOT; ++s)
-#pragma unroll
-                        for (int i = 0; i < VEC; ++i)
-                            acc[s].v[i] = live ? fmaf(vj[u], x[u][s].v[i], acc[s].v[i]) : acc[s].v[i];
-                }
-            }
+                for (int i = 0; i < VEC; ++i) acc[s].v[i] = 0.0f;
         }
         if (mine) {
             const int64_t out_row = row_map ? (int64_t)__ldg(row_map + row) : row;
@@ -491,96 +579,18 @@ spmm_bulk_kernel(const int* __restrict__ row_ptr, const int* __restrict__ col_id
 }
 
 // ---------------------------------------------------------------------------------------------
-// Long rows, phase 1: one warp per piece.  The 32/GROUP lane groups take the piece's entries
-// round-robin and are combined with xor-shuffles in a fixed pattern.
-// partials[piece, ldp] (ldp = round_up(F,4)).
-// ---------------------------------------------------------------------------------------------
+// Stand-alone launch of the piece work (used by the bulk-copy variant; the row kernel runs the
+// pieces inside its own grid).
 template <int VEC, int NSLOT, int GROUP, int UNROLL, int THREADS>
 __global__ void __launch_bounds__(THREADS)
 spmm_chunk_kernel(const int* __restrict__ row_ptr, const int* __restrict__ col_idx,
                   const float* __restrict__ val, const float* __restrict__ B, int64_t ldb,
                   const int* __restrict__ chunk_row, const int* __restrict__ chunk_begin,
                   int n_chunks, int chunk, float* __restrict__ partials, int ldp, int F) {
-    constexpr int NGROUPS = 32 / GROUP;
-    constexpr int WARPS = THREADS / 32;
-    const int lane = threadIdx.x & 31;
-    const int g = lane / GROUP;
-    const int gl = lane % GROUP;
-    const int piece = blockIdx.x * WARPS + (threadIdx.x >> 5);
+    const int piece = blockIdx.x * (THREADS / 32) + (threadIdx.x >> 5);
     if (piece >= n_chunks) return;  // warp-uniform
-    const int f_base = blockIdx.y * (GROUP * NSLOT * VEC);
-    const int row = __ldg(chunk_row + piece);
-    const int begin = __ldg(chunk_begin + piece);
-    const int end = min(begin + chunk, __ldg(row_ptr + row + 1));
-
-    int fo[NSLOT];
-    bool fok[NSLOT];
-#pragma unroll
-    for (int s = 0; s < NSLOT; ++s) {
-        fo[s] = f_base + (s * GROUP + gl) * VEC;
-        fok[s] = fo[s] < F;
-    }
-    Vec<VEC> acc[NSLOT];
-#pragma unroll
-    for (int s = 0; s < NSLOT; ++s)
-#pragma unroll
-        for (int i = 0; i < VEC; ++i) acc[s].v[i] = 0.0f;
-
-    // 32 entries per outer step: lane l holds entry base+l; group g consumes entries with
-    // (index % NGROUPS) == g.
-    for (int base = begin; base < end; base += 32) {
-        int c = 0;
-        float v = 0.0f;
-        if (base + lane < end) {
-            c = ld_stream(col_idx + base + lane);
-            v = ld_stream(val + base + lane);
-        }
-        const int cnt = min(32, end - base);
-        for (int j = 0; j < cnt; j += NGROUPS * UNROLL) {
-            int cj[UNROLL];
-            float vj[UNROLL];
-#pragma unroll
-            for (int u = 0; u < UNROLL; ++u) {
-                const int src = j + u * NGROUPS + g;
-                cj[u] = __shfl_sync(0xffffffffu, c, src & 31);
-                vj[u] = __shfl_sync(0xffffffffu, v, src & 31);
-                if (src >= cnt) vj[u] = 0.0f, cj[u] = -1;
-            }
-            Vec<VEC> x[UNROLL][NSLOT];
-#pragma unroll
-            for (int u = 0; u < UNROLL; ++u) {
-                const float* src = B + (int64_t)cj[u] * ldb;
-#pragma unroll
-                for (int s = 0; s < NSLOT; ++s) {
-                    if (cj[u] >= 0 && fok[s]) {
-                        x[u][s] = Vec<VEC>::gather(src + fo[s]);
-                    } else {
-#pragma unroll
-                        for (int i = 0; i < VEC; ++i) x[u][s].v[i] = 0.0f;
-                    }
-                }
-            }
-#pragma unroll
-            for (int u = 0; u < UNROLL; ++u)
-#pragma unroll
-                for (int s = 0; s < NSLOT; ++s)
-#pragma unroll
-                    for (int i = 0; i < VEC; ++i) acc[s].v[i] = fmaf(vj[u], x[u][s].v[i], acc[s].v[i]);
-        }
-    }
-    if (NGROUPS > 1) {
-#pragma unroll
-        for (int o = GROUP; o < 32; o <<= 1)
-#pragma unroll
-            for (int s = 0; s < NSLOT; ++s)
-#pragma unroll
-                for (int i = 0; i < VEC; ++i) acc[s].v[i] += __shfl_xor_sync(0xffffffffu, acc[s].v[i], o);
-    }
-    if (g == 0) {
-#pragma unroll
-        for (int s = 0; s < NSLOT; ++s)
-            if (fok[s]) acc[s].store(partials + (int64_t)piece * ldp + fo[s]);
-    }
+    process_piece<VEC, NSLOT, GROUP, UNROLL>(row_ptr, col_idx, val, B, ldb, chunk_row, chunk_begin, piece, chunk,
+                                             partials, ldp, F, blockIdx.y * (GROUP * NSLOT * VEC));
 }
 
 // Long rows, phase 2: one CTA per long row; thread t owns feature t (strided), sums the row's
@@ -621,7 +631,6 @@ static int env_int(const char* name, int dflt) {
 // kernel for wide rows (measured SLOWER than the register kernel on B200: 102 vs 61 ms on the
 // products shape — one 400-byte bulk copy costs ~23 cycles of TMA issue per SM — so it is off by
 // default), GNNTF_SPMM_ROWS the rows per chunk.
-static int rows_minb() { static int v = env_int("GNNTF_SPMM_MINB", 5); return v; }
 static int rows_blocks_per_cta() { static int v = std::max(1, env_int("GNNTF_SPMM_BPC", 8)); return v; }
 static int bulk_mode() { static int v = env_int("GNNTF_SPMM_BULK", 0); return v; }
 static int bulk_rows_per_chunk() { static int v = std::max(1, std::min(31, env_int("GNNTF_SPMM_ROWS", 16))); return v; }
@@ -641,30 +650,24 @@ static int launch_cfg(const gnntf_csr_t* A, const float* B, int64_t ldb, const E
         // waves; small graphs (Cora: 43 row blocks) keep one block per CTA
         const int64_t row_blocks = ceil_div(A->n_rows, ROWS_PER_CTA);
         const int bpc = (int)std::max<int64_t>(1, std::min<int64_t>(rows_blocks_per_cta(), row_blocks / ((int64_t)kNumSMs * 5 * 4)));
-        dim3 grid((unsigned)ceil_div(A->n_rows, (int64_t)ROWS_PER_CTA * bpc), gy);
-        if (rows_minb() >= 6)
-            spmm_rows_kernel<VEC, NSLOT, GROUP, UNROLL, THREADS, 6><<<grid, THREADS, 0, st>>>(
-                A->row_ptr, A->col_idx, A->val, A->row_map, B, ldb, (int)A->n_rows, thr, bpc, epi);
-        else if (rows_minb() == 4)
-            spmm_rows_kernel<VEC, NSLOT, GROUP, UNROLL, THREADS, 4><<<grid, THREADS, 0, st>>>(
-                A->row_ptr, A->col_idx, A->val, A->row_map, B, ldb, (int)A->n_rows, thr, bpc, epi);
-        else
-            spmm_rows_kernel<VEC, NSLOT, GROUP, UNROLL, THREADS, 5><<<grid, THREADS, 0, st>>>(
-                A->row_ptr, A->col_idx, A->val, A->row_map, B, ldb, (int)A->n_rows, thr, bpc, epi);
-        GNNTF_LAUNCH_CHECK();
-    }
-    if (A->n_long > 0) {
+        // the pieces of split rows ride in the same grid, ahead of the ordinary rows
+        PieceArgs pieces{};
+        int piece_ctas = 0;
         const int ldp = (int)round_up(F, 4);
-        constexpr int CU = (NSLOT >= 4) ? 2 : 4;
-        dim3 grid((unsigned)ceil_div(A->n_chunks, THREADS / 32), gy);
-        spmm_chunk_kernel<VEC, NSLOT, GROUP, CU, THREADS><<<grid, THREADS, 0, st>>>(
-            A->row_ptr, A->col_idx, A->val, B, ldb, A->chunk_row, A->chunk_begin, A->n_chunks,
-            A->chunk, A->partials, ldp, F);
+        if (A->n_long > 0) {
+            pieces = PieceArgs{A->chunk_row, A->chunk_begin, A->n_chunks, A->chunk, A->partials, ldp};
+            piece_ctas = (int)ceil_div(A->n_chunks, THREADS / 32);
+        }
+        dim3 grid((unsigned)(piece_ctas + ceil_div(A->n_rows, (int64_t)ROWS_PER_CTA * bpc)), gy);
+        spmm_rows_kernel<VEC, NSLOT, GROUP, UNROLL, THREADS, 5><<<grid, THREADS, 0, st>>>(
+            A->row_ptr, A->col_idx, A->val, A->row_map, B, ldb, (int)A->n_rows, thr, bpc, piece_ctas, pieces, epi);
         GNNTF_LAUNCH_CHECK();
-        spmm_long_reduce_kernel<<<A->n_long, 128, 0, st>>>(A->long_row, A->long_first_chunk,
-                                                          A->long_n_chunks, A->row_map, A->partials,
-                                                          ldp, epi);
-        GNNTF_LAUNCH_CHECK();
+        if (A->n_long > 0) {
+            spmm_long_reduce_kernel<<<A->n_long, 128, 0, st>>>(A->long_row, A->long_first_chunk,
+                                                              A->long_n_chunks, A->row_map, A->partials,
+                                                              ldp, epi);
+            GNNTF_LAUNCH_CHECK();
+        }
     }
     return GNNTF_OK;
 }

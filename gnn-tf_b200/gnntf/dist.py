@@ -336,7 +336,7 @@ class ShardedPropagator:
         per_step = 1 if self.plan.world > 1 else 0  # pack
         for st in (self.owned, self.halo_part):
             if st.n > 0 and st.nnz > 0 or st is self.owned:
-                per_step += 3 if st.n_long > 0 else 1
+                per_step += 2 if st.n_long > 0 else 1
         return K * per_step * len(self.parts)
 
     # -- one half: exchange and compute -----------------------------------------------------
