@@ -147,7 +147,7 @@ def make_workload(args, device):
 def config_dict(args, n, E, nnz, F):
     return {"workload": f"APPNP K={K_ITER} a={ALPHA} on {args.workload}-shaped synthetic graph", "nodes": n, "edges": E,
             "nnz": nnz, "features": F, "iterations": K_ITER, "alpha": ALPHA, "ordering": args.ordering,
-            "scale": args.scale, "normalisation": "symmetric, eval mode (prebuilt)",
+            "scale": args.scale, "reorder": bool(getattr(args, "reorder", False)), "normalisation": "symmetric, eval mode (prebuilt)",
             "l2": "no explicit flush: per-step working set (CSR + 3 feature matrices) exceeds the 126 MB L2"
                   if step_bytes(n, nnz, F) > 3 * 126e6 else "working set fits L2: flushed by a 256 MB write between steps"}
 
@@ -234,6 +234,8 @@ def gpu_arm(args):
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     adj = gnntf.edges2adj(edges, None, n)
+    if args.reorder:
+        adj = adj.reordered()
     A = adj.normalized("symmetric")
     torch.cuda.synchronize()
     build_s = time.perf_counter() - t0
@@ -254,7 +256,7 @@ def gpu_arm(args):
         log(f"[rank {rank} = row group {grid.r}/{R}, column group {grid.c}/{C}] rows {prop.lo}:{prop.hi} cols {c0}:{c1} "
             f"nnz {prop.nnz_local} halo rows {prop.n_halo} owned-column entries {prop.owned.nnz} "
             f"halo-column entries {prop.halo_part.nnz} (rows {prop.halo_part.n})")
-        H0_local = H0[prop.lo:prop.hi, c0:c1].contiguous()
+        H0_local = (H0 if adj.perm is None else H0.index_select(0, adj.perm))[prop.lo:prop.hi, c0:c1].contiguous()
         run = lambda: prop.propagate(H0_local, ALPHA, K_ITER)  # noqa: E731
         launches_per_step = prop.launches_per_propagation(K_ITER)
         sharding = (f"{R} row groups (contiguous node ranges balanced by nnz; halo rows by NCCL all-to-all inside a column "
@@ -263,7 +265,12 @@ def gpu_arm(args):
     else:
         out = torch.empty_like(H0)
         scratch = torch.empty_like(H0)
-        run = lambda: ops.propagate_raw(A, H0, ALPHA, K_ITER, out=out, scratch=scratch)  # noqa: E731
+        if args.reorder:  # features live in external node order: the permutation in/out is part of the step
+            def run():
+                with torch.no_grad():
+                    return gnntf.appnp_propagate(A, H0, ALPHA, K_ITER)
+        else:
+            run = lambda: ops.propagate_raw(A, H0, ALPHA, K_ITER, out=out, scratch=scratch)  # noqa: E731
         launches_per_step = K_ITER * (2 if adj.csr.n_long > 0 else 1)  # row kernel (pieces ride in its grid) + long-row reduce
     flush = None
     if step_bytes(n, nnz, F) <= 3 * 126e6:
@@ -393,6 +400,7 @@ def main():
     ap.add_argument("--features", type=int, default=0, help="feature width (default: the shape's)")
     ap.add_argument("--scale", type=float, default=1.0, help="shrink the graph (tests only; 1.0 = BASELINE size)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--reorder", action="store_true", help="locality-restoring internal node order (gnntf/reorder.py); its cost is part of the build time")
     ap.add_argument("--grid", default="", help="multi-GPU layout ROWSxCOLS (default: gnntf.dist.choose_grid)")
     ap.add_argument("--nccl-exchange", action="store_true", help="multi-GPU: halo rows by NCCL all-to-all instead of the fused peer-memory push")
     ap.add_argument("--halves", type=int, default=0, help="multi-GPU: feature-column chains to pipeline (0 = default)")

@@ -231,6 +231,38 @@ __global__ void scale_values_kernel(const int32_t* __restrict__ row_ptr, const i
     }
 }
 
+// One warp per node; positions (9.8 MB at products scale) stay L2-resident.
+__global__ void arrange_sweep_kernel(const int32_t* __restrict__ row_ptr, const int32_t* __restrict__ col_idx,
+                                     const float* __restrict__ theta_in, float eps, float* __restrict__ theta_out,
+                                     int64_t n) {
+    const float two_pi = 6.283185307179586f;
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t i = warp; i < n; i += nwarps) {
+        const int s = row_ptr[i], e = row_ptr[i + 1];
+        const float ti = theta_in[i];
+        float num = 0.0f, den = 0.0f;
+        for (int p = s + lane; p < e; p += 32) {
+            float d = __ldg(theta_in + col_idx[p]) - ti;
+            d -= two_pi * rintf(d * (1.0f / two_pi));  // signed circular offset in (-pi, pi]
+            const float w = 1.0f / (fabsf(d) + eps);
+            num += w * d;
+            den += w;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            num += __shfl_xor_sync(0xffffffffu, num, o);
+            den += __shfl_xor_sync(0xffffffffu, den, o);
+        }
+        if (lane == 0) {
+            float t = (den > 0.0f) ? ti + num / den : ti;
+            t -= two_pi * floorf(t * (1.0f / two_pi));
+            theta_out[i] = t;
+        }
+    }
+}
+
 }  // namespace gnntf
 
 using namespace gnntf;
@@ -336,5 +368,16 @@ extern "C" int gnntf_normalize_f32(const int32_t* row_ptr, const int32_t* col_id
                                                            norm_val_coo);
         GNNTF_LAUNCH_CHECK();
     }
+    return GNNTF_OK;
+}
+
+extern "C" int gnntf_arrange_sweep_f32(const int32_t* row_ptr, const int32_t* col_idx, const float* theta_in,
+                                       float eps, float* theta_out, int64_t n, void* stream) {
+    if (n < 0 || n > 0x7ffffffeLL || !(eps > 0.0f)) return GNNTF_E_SIZE;
+    if (n == 0) return GNNTF_OK;
+    if (row_ptr == nullptr || theta_in == nullptr || theta_out == nullptr) return GNNTF_E_NULL;
+    const int grid = (int)std::min<int64_t>(ceil_div(n, 8), (int64_t)kNumSMs * 16);
+    arrange_sweep_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(row_ptr, col_idx, theta_in, eps, theta_out, n);
+    GNNTF_LAUNCH_CHECK();
     return GNNTF_OK;
 }

@@ -21,7 +21,7 @@ ACT_IDENTITY, ACT_RELU = 0, 1
 # every symbol include/gnntf_b200.h declares (checked by tests/test_abi.py)
 SYMBOLS = [
     "gnntf_abi_version", "gnntf_status_str", "gnntf_csr_build_ws_bytes", "gnntf_csr_build",
-    "gnntf_normalize_f32", "gnntf_spmm_plan_count", "gnntf_spmm_plan_fill", "gnntf_spmm_f32", "gnntf_spmm_acc_f32",
+    "gnntf_normalize_f32", "gnntf_arrange_sweep_f32", "gnntf_spmm_plan_count", "gnntf_spmm_plan_fill", "gnntf_spmm_f32", "gnntf_spmm_acc_f32",
     "gnntf_appnp_step_f32", "gnntf_appnp_propagate_f32", "gnntf_appnp_propagate_multi_f32",
     "gnntf_appnp_propagate_bwd_f32", "gnntf_appnp_propagate_host_f32",
     "gnntf_halo_pack_f32", "gnntf_halo_push_f32", "gnntf_ipc_alloc", "gnntf_ipc_open", "gnntf_ipc_close", "gnntf_ipc_free",
@@ -67,6 +67,7 @@ def lib():
     L.gnntf_normalize_f32.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64,
                                       c_int, c_void_p, c_float, c_int, c_int, c_void_p, c_void_p,
                                       c_void_p, c_void_p, c_void_p, c_void_p]
+    L.gnntf_arrange_sweep_f32.argtypes = [c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_int64, c_void_p]
     L.gnntf_spmm_plan_count.argtypes = [c_void_p, c_int64, c_int32, c_int32, c_void_p, c_void_p]
     L.gnntf_spmm_plan_fill.argtypes = [c_void_p, c_int64, c_int32, c_int32, c_void_p, c_void_p, c_void_p,
                                        c_void_p, c_void_p, c_void_p, c_void_p]

@@ -49,6 +49,17 @@ def _pad4(x):
     return out, F
 
 
+def _perm_in(adj, x):
+    """External node order -> the adjacency's internal order (identity unless ``reordered()``)."""
+    perm = adj.base.perm if not isinstance(adj, (list, tuple)) else adj[0].base.perm
+    return x if perm is None else x.index_select(0, perm)
+
+
+def _perm_out(adj, x):
+    inv = adj.base.inv if not isinstance(adj, (list, tuple)) else adj[0].base.inv
+    return x if inv is None else x.index_select(0, inv)
+
+
 def _ld(x):
     return x.stride(0) if x.shape[0] > 1 else max(x.shape[1], x.stride(0))
 
@@ -68,15 +79,15 @@ class _SpMM(torch.autograd.Function):
     @staticmethod
     def forward(ctx, adj, H):
         ctx.adj = adj
-        return spmm_raw(adj.struct(H.shape[1]), adj.base.n, H)
+        return _perm_out(adj, spmm_raw(adj.struct(H.shape[1]), adj.base.n, _perm_in(adj, H)))
 
     @staticmethod
     def backward(ctx, g):
         adj = ctx.adj
         if not ctx.needs_input_grad[1]:
             return None, None  # e.g. the constant feature matrix of the first GCN layer
-        g = _dense(g)
-        return None, spmm_raw(adj.struct_T(g.shape[1]), adj.base.n, g)
+        g = _perm_in(adj, _dense(g))
+        return None, _perm_out(adj, spmm_raw(adj.struct_T(g.shape[1]), adj.base.n, g))
 
 
 def sparse_dense_matmul(adj, H):
@@ -103,9 +114,10 @@ def _step_raw(struct, H_in, H0, alpha, feat_keep=None, p_scale=1.0, act=nat.ACT_
 class _Step(torch.autograd.Function):
     @staticmethod
     def forward(ctx, adj, H, H0, alpha, feat_keep, p_scale, relu):
-        H, H0 = H.contiguous(), H0.contiguous()
-        out = _step_raw(adj.struct(H.shape[1]), H, H0, alpha, feat_keep, p_scale,
-                        nat.ACT_RELU if relu else nat.ACT_IDENTITY)
+        H, H0 = _perm_in(adj, H.contiguous()), _perm_in(adj, H0.contiguous())
+        keep_internal = _perm_in(adj, feat_keep) if feat_keep is not None else None
+        out = _perm_out(adj, _step_raw(adj.struct(H.shape[1]), H, H0, alpha, keep_internal, p_scale,
+                                       nat.ACT_RELU if relu else nat.ACT_IDENTITY))
         ctx.adj, ctx.alpha, ctx.p_scale, ctx.relu = adj, alpha, p_scale, relu
         ctx.save_for_backward(feat_keep if feat_keep is not None else torch.empty(0), out if relu else torch.empty(0))
         return out
@@ -118,7 +130,8 @@ class _Step(torch.autograd.Function):
             g = g * (out > 0)
         if keep.numel():
             g = g * keep.to(g.dtype) * ctx.p_scale
-        dH = spmm_raw(ctx.adj.struct_T(g.shape[1]), ctx.adj.base.n, g).mul_(1.0 - ctx.alpha) \
+        dH = _perm_out(ctx.adj, spmm_raw(ctx.adj.struct_T(g.shape[1]), ctx.adj.base.n,
+                                         _perm_in(ctx.adj, g.contiguous())).mul_(1.0 - ctx.alpha)) \
             if ctx.needs_input_grad[1] else None
         dH0 = g * ctx.alpha if ctx.needs_input_grad[2] else None
         return None, dH, dH0, None, None, None, None
@@ -162,15 +175,15 @@ def propagate_raw(adjs, H0, alpha, K, out=None, scratch=None):
 class _Propagate(torch.autograd.Function):
     @staticmethod
     def forward(ctx, adjs, H0, alpha, K):
-        H0p, F = _pad4(H0.contiguous())
+        H0p, F = _pad4(_perm_in(adjs, H0.contiguous()))
         ctx.adjs, ctx.alpha, ctx.K = adjs, alpha, K
-        out = propagate_raw(adjs, H0p, alpha, K)
+        out = _perm_out(adjs, propagate_raw(adjs, H0p, alpha, K))
         return out if out.shape[1] == F else out[:, :F].contiguous()
 
     @staticmethod
     def backward(ctx, g):
         L = nat.lib()
-        g, F_orig = _pad4(g.contiguous())
+        g, F_orig = _pad4(_perm_in(ctx.adjs, g.contiguous()))
         F, ld, K = g.shape[1], _ld(g), ctx.K
         adjs = ctx.adjs if isinstance(ctx.adjs, (list, tuple)) else [ctx.adjs] * K
         arr = _struct_array([a.struct_T(F) for a in adjs])
@@ -178,6 +191,7 @@ class _Propagate(torch.autograd.Function):
         scratch = torch.empty((2,) + tuple(g.shape), dtype=g.dtype, device=g.device) if K > 1 else None
         nat.check(L.gnntf_appnp_propagate_bwd_f32(arr, K, nat.ptr(g), nat.ptr(dH0), nat.ptr(scratch), ld, F,
                                                   float(ctx.alpha), nat.stream_ptr()), "appnp_propagate_bwd")
+        dH0 = _perm_out(ctx.adjs, dH0)
         return None, (dH0 if F == F_orig else dH0[:, :F_orig].contiguous()), None, None
 
 
@@ -198,6 +212,14 @@ def appnp_propagate_host(adj, H0_host, alpha=0.1, iterations=10, out_host=None, 
     L = nat.lib()
     adj = _as_norm(adj)
     n, F = H0_host.shape
+    if adj.base.perm is not None:  # reordered adjacency: permute on the device at both ends
+        if out_host is None:
+            out_host = torch.empty((n, F), dtype=torch.float32, pin_memory=True)
+        H0 = H0_host.to("cuda", non_blocking=True)
+        out = _perm_out(adj, propagate_raw(adj, _perm_in(adj, H0), alpha, iterations))
+        out_host.copy_(out, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return out_host
     if bufs is None:
         bufs = [torch.empty((n, F), dtype=torch.float32, device="cuda") for _ in range(3)]
     if out_host is None:

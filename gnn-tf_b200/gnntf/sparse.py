@@ -114,13 +114,25 @@ class SparseAdjacency:
     graph_manipulation.py:31 (same order, duplicates kept).  ``csr`` is the derived kernel view.
     """
 
-    def __init__(self, edges, weights, n, directed=False):
+    def __init__(self, edges, weights, n, directed=False, _source=None, _order=None):
         _require_cuda()
         self.n = int(n)
         self.directed = bool(directed)
         self.edges = edges.contiguous()
         self.weights = None if weights is None else weights.contiguous()
-        self.indices, self.values, self.csr, self.raw_val = build_csr(self.edges, self.weights, self.n, directed)
+        # a reordered view (see reordered()): internal CSR over relabelled nodes, externally visible
+        # COO fields are the source's, untouched
+        self.source = _source
+        self.perm = _order                       # int64 [n]: internal position -> external node id
+        self.inv = None
+        if _order is not None:
+            self.inv = torch.empty_like(_order)
+            self.inv[_order] = torch.arange(self.n, dtype=_order.dtype, device=_order.device)
+        coo = _source is None
+        self.indices, self.values, self.csr, self.raw_val = build_csr(self.edges, self.weights, self.n, directed,
+                                                                      want_coo=coo)
+        if not coo:
+            self.indices, self.values = _source.indices, _source.values
         self.n_graph = self.csr.nnz
         self.dense_shape = (self.n, self.n)
         self.shape = self.dense_shape
@@ -128,11 +140,30 @@ class SparseAdjacency:
         self._with_eye = None
         self._csc = None
 
+    def reordered(self, power_iters=100, sweeps=30, seed=0, order=None):
+        """Same graph with a locality-restoring INTERNAL node order (gnntf/reorder.py).  Everything a
+        user can see keeps the reference's numbering: ``indices``/``values`` are this object's, features
+        go in and results come out in external node order (the ops permute at the boundary).  COO
+        storage order — hence edge-dropout masks and the accumulation order inside every row — is
+        unchanged, so results are identical to the un-reordered adjacency."""
+        if self.perm is not None:
+            return self
+        if order is None:
+            from .reorder import arrangement_order
+            order = arrangement_order(self, power_iters, sweeps, seed)
+        order = order.to(device=self.edges.device, dtype=torch.int64).contiguous()
+        inv = torch.empty_like(order)
+        inv[order] = torch.arange(self.n, dtype=torch.int64, device=order.device)
+        return SparseAdjacency(inv[self.edges], self.weights, self.n, self.directed, _source=self, _order=order)
+
     # -- structure variants --------------------------------------------------------------
     def with_eye(self):
         """CSR of the list with ``tf.sparse.eye`` appended (gnn.py:39,49), built on first use."""
         if self._with_eye is None:
-            self._with_eye = build_csr(self.edges, self.weights, self.n, self.directed, add_eye=True)
+            idx, val, csr, raw = build_csr(self.edges, self.weights, self.n, self.directed, add_eye=True)
+            if self.source is not None:  # externally visible indices stay in external numbering
+                idx = torch.cat([self.source.indices, torch.arange(self.n, device=idx.device).repeat(2, 1).T.contiguous()])
+            self._with_eye = (idx, val, csr, raw)
         return self._with_eye
 
     def csc(self):

@@ -127,6 +127,18 @@ int gnntf_normalize_f32(const int32_t* row_ptr, const int32_t* col_idx, const fl
                         float* norm_val_coo, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Locality-restoring node order (builder-side; external indices are never changed).
+ * One sweep of a robust 1-D circular arrangement: every node moves to the weighted circular mean
+ * of its neighbours' positions, weights 1/(|offset| + eps) (iteratively re-weighted least
+ * absolute deviation: near neighbours dominate, far ones are ignored):
+ *   theta_out[i] = theta_in[i] + sum_j w_ij * wrap(theta_in[j] - theta_in[i]) / sum_j w_ij   (mod 2*pi)
+ * theta in [0, 2*pi).  The host re-ranks the angles between sweeps and seeds them with the angle
+ * of the two leading non-trivial eigenvectors of the normalised adjacency (gnntf/reorder.py).
+ * ---------------------------------------------------------------------------------------- */
+int gnntf_arrange_sweep_f32(const int32_t* row_ptr, const int32_t* col_idx, const float* theta_in,
+                            float eps, float* theta_out, int64_t n, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * Long-row plan for the SpMM kernels (two calls so the caller can size the arrays).
  * counts: int32 [2] device = {n_long, n_chunks}.
  * ---------------------------------------------------------------------------------------- */

@@ -534,3 +534,50 @@ def test_spmm_short_rows_mapping_and_accumulate(F):
     nat.check(nat.lib().gnntf_spmm_acc_f32(ctypes.byref(s), nat.ptr(torch.from_numpy(H).cuda()), F, nat.ptr(C), F, F, 0.9,
                                            nat.stream_ptr()))
     oracle.assert_close(_np(C), C0 + np.float32(0.9) * P, what="accumulate pass")
+
+
+# ------------------------------------------------------------------------------------------
+# Locality-restoring internal node order (gnntf/reorder.py)
+# ------------------------------------------------------------------------------------------
+def test_reordered_adjacency_gives_identical_results_and_keeps_external_indices():
+    gnntf = _gnntf()
+    n, edges = synthetic.shaped_edges("arxiv", seed=0, ordering="random", device="cuda", scale=0.2)
+    w = torch.rand(edges.shape[0], device="cuda") + 0.5
+    adj = gnntf.edges2adj(edges, w, n)
+    radj = adj.reordered(power_iters=30, sweeps=10)
+    assert radj.perm is not None and torch.equal(torch.sort(radj.perm).values, torch.arange(n, device="cuda"))
+    assert torch.equal(radj.indices, adj.indices) and torch.equal(radj.values, adj.values)   # what the user sees
+    assert radj.reordered() is radj
+    H0 = synthetic.features(n, 47, 1, "cuda").requires_grad_(True)
+    H1 = H0.detach().clone().requires_grad_(True)
+    g = synthetic.features(n, 47, 2, "cuda")
+    out_a = gnntf.appnp_propagate(adj.normalized("symmetric"), H0, 0.1, 10)
+    out_b = gnntf.appnp_propagate(radj.normalized("symmetric"), H1, 0.1, 10)
+    oracle.assert_close(_np(out_b), _np(out_a), rtol=1e-6, what="reordered forward")
+    out_a.backward(g)
+    out_b.backward(g)
+    oracle.assert_close(_np(H1.grad), _np(H0.grad), rtol=1e-6, what="reordered backward")
+    X = synthetic.features(n, 24, 3, "cuda")
+    oracle.assert_close(_np(gnntf.sparse_dense_matmul(radj.normalized("symmetric"), X)),
+                        _np(gnntf.sparse_dense_matmul(adj.normalized("symmetric"), X)), rtol=1e-6, what="reordered SpMM")
+    # masked (training-mode) normalisation: COO order is unchanged, so the same mask means the same matrix
+    keep = torch.rand(adj.n_graph, device="cuda") >= 0.5
+    oracle.assert_close(_np(radj.normalized("symmetric", keep_mask=keep, rate=0.5).values),
+                        _np(adj.normalized("symmetric", keep_mask=keep, rate=0.5).values), rtol=1e-6, what="masked values")
+
+
+def test_arrangement_recovers_hidden_locality():
+    """A randomly relabelled graph with multi-scale locality: after reordering, edges span far
+    fewer positions (the property the SpMM's L2 hit rate depends on)."""
+    gnntf = _gnntf()
+    n, edges = synthetic.shaped_edges("products", seed=0, ordering="random", device="cuda", scale=0.02)
+    adj = gnntf.edges2adj(edges, None, n)
+    radj = adj.reordered()
+
+    def median_span(e):
+        d = (e[:, 0] - e[:, 1]).abs()
+        return torch.minimum(d, n - d).float().median().item()
+    before, after = median_span(edges), median_span(radj.edges)
+    n_loc, e_loc = synthetic.shaped_edges("products", seed=0, ordering="local", device="cuda", scale=0.02)
+    native = median_span(e_loc)
+    assert after < before / 20 and after < 3 * native, (before, after, native)
