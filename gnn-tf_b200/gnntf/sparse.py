@@ -202,36 +202,45 @@ class NormalizedAdjacency:
     """Return type of ``GNN.get_adjacency`` (gnn.py:36-50): same index list, normalised values."""
 
     def __init__(self, base, indices, csr, raw_val, mode, eye_mode, keep_mask, rate):
-        L = nat.lib()
         self.base, self.indices, self.csr = base, indices, csr
         self.dense_shape = self.shape = base.dense_shape
         self.mode, self.eye_mode = mode, eye_mode
         n, nnz, dev = base.n, csr.nnz, raw_val.device
         self.has_mask = keep_mask is not None
-        scale = 1.0
+        self._scale = 1.0
         if self.has_mask:
             keep_mask = keep_mask.to(device=dev, dtype=torch.uint8).contiguous()
             if keep_mask.numel() != base.n_graph:
                 raise Exception(f"edge keep-mask must have one entry per COO entry ({base.n_graph}), got {keep_mask.numel()}")
-            scale = 1.0 / (1.0 - float(rate))
+            self._scale = 1.0 / (1.0 - float(rate))
+        self._keep, self._raw_val = keep_mask, raw_val
         f32 = dict(dtype=torch.float32, device=dev)
         self.deg = torch.zeros(n, **f32)
         self.dinv = torch.zeros(n, **f32)
         self.val = torch.empty(nnz, **f32)
         want_T = (self.has_mask or mode == "bipartite") and not base.directed  # row-only scaling is not symmetric
         self._val_T = torch.empty(nnz, **f32) if want_T else None
-        self._values_coo = torch.empty(nnz, **f32)
-        nat.check(L.gnntf_normalize_f32(nat.ptr(csr.row_ptr), nat.ptr(csr.col_idx), nat.ptr(raw_val),
-                                        nat.ptr(csr.coo_pos), n, nnz, base.n_graph, int(base.directed),
-                                        nat.ptr(keep_mask), scale, nat.NORM[mode], nat.EYE[eye_mode],
-                                        nat.ptr(self.deg), nat.ptr(self.dinv), nat.ptr(self.val),
-                                        nat.ptr(self._val_T), nat.ptr(self._values_coo), nat.stream_ptr()),
-                  "normalize")
+        self._values_coo = None   # COO-order values are produced on first use of .values
+        self._run(None)
         self._T = None
+
+    def _run(self, values_coo):
+        L = nat.lib()
+        base, csr = self.base, self.csr
+        nat.check(L.gnntf_normalize_f32(nat.ptr(csr.row_ptr), nat.ptr(csr.col_idx), nat.ptr(self._raw_val),
+                                        nat.ptr(csr.coo_pos), base.n, csr.nnz, base.n_graph, int(base.directed),
+                                        nat.ptr(self._keep), self._scale, nat.NORM[self.mode], nat.EYE[self.eye_mode],
+                                        nat.ptr(self.deg), nat.ptr(self.dinv), nat.ptr(self.val),
+                                        nat.ptr(self._val_T), nat.ptr(values_coo), nat.stream_ptr()),
+                  "normalize")
 
     @property
     def values(self):
-        """COO-order values: the ``.values`` of the SparseTensor the reference returns."""
+        """COO-order values: the ``.values`` of the SparseTensor the reference returns.  Computed on
+        first use (the kernels only need CSR order; a training forward builds K of these objects)."""
+        if self._values_coo is None:
+            self._values_coo = torch.empty(self.csr.nnz, dtype=torch.float32, device=self.val.device)
+            self._run(self._values_coo)
         return self._values_coo
 
     def struct(self, F):
@@ -248,7 +257,7 @@ class NormalizedAdjacency:
                 if self.eye_mode != "none":
                     raise Exception("transposed directed adjacency with add_eye is not supported")
                 csr_t = self.base.csc()
-                self._T = (csr_t, self._values_coo[csr_t.coo_pos.long()].contiguous())
+                self._T = (csr_t, self.values[csr_t.coo_pos.long()].contiguous())
         return self._T
 
     def struct_T(self, F):
