@@ -581,3 +581,33 @@ def test_arrangement_recovers_hidden_locality():
     n_loc, e_loc = synthetic.shaped_edges("products", seed=0, ordering="local", device="cuda", scale=0.02)
     native = median_span(e_loc)
     assert after < before / 20 and after < 3 * native, (before, after, native)
+
+
+def test_bulk_copy_variant_parity_in_subprocess():
+    """The TMA bulk-copy SpMM variant (off by default, GNNTF_SPMM_BULK=1 is read once per process)
+    stays parity-green: wide rows, split rows, empty rows, K-step loop."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = r'''
+import sys, numpy as np, torch
+sys.path.insert(0, "%s/gnn-tf_b200"); sys.path.insert(0, "%s/oracle")
+import gnntf, gnntf_oracle as oracle
+rng = np.random.default_rng(0)
+n = 4000
+hub = np.stack([np.zeros(1500, np.int64), rng.integers(1, n - 50, 1500)], 1)
+edges = np.concatenate([hub, rng.integers(1, n - 50, size=(30000, 2))])
+w = rng.random(edges.shape[0]).astype(np.float32) + 0.5
+adj = gnntf.edges2adj(edges, w, n)
+A = adj.normalized("symmetric")
+idx, val, _ = oracle.graph2adj_arrays(edges, w, n)
+for F in (100, 128, 256, 500):
+    H0 = rng.standard_normal((n, F)).astype(np.float32)
+    got = gnntf.appnp_propagate(A, torch.from_numpy(H0).cuda(), 0.1, 3).cpu().numpy()
+    oracle.assert_close(got, oracle.appnp_propagate(idx, val, n, H0, 0.1, 3)[-1], what="bulk F=%%d" %% F)
+print("BULK-OK")
+''' % (root, root)
+    env = dict(os.environ, GNNTF_SPMM_BULK="1")
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=600)
+    assert out.returncode == 0 and "BULK-OK" in out.stdout, out.stdout[-1500:] + out.stderr[-1500:]
