@@ -611,3 +611,25 @@ print("BULK-OK")
     env = dict(os.environ, GNNTF_SPMM_BULK="1")
     out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=600)
     assert out.returncode == 0 and "BULK-OK" in out.stdout, out.stdout[-1500:] + out.stderr[-1500:]
+
+
+def test_propagation_is_bitwise_deterministic():
+    """No float atomics on the undirected path: two runs (and a rebuilt adjacency) give identical bits,
+    including rows split into pieces and the backward pass."""
+    gnntf = _gnntf()
+    n, edges = synthetic.shaped_edges("arxiv", seed=0, device="cuda", scale=0.5)
+    H0 = synthetic.features(n, 100, 1, "cuda")
+    g = synthetic.features(n, 100, 2, "cuda")
+    outs, grads = [], []
+    for _ in range(2):
+        adj = gnntf.edges2adj(edges, None, n)
+        assert adj.csr.n_long > 0
+        A = adj.normalized("symmetric")
+        for _ in range(2):
+            h = H0.clone().requires_grad_(True)
+            out = gnntf.appnp_propagate(A, h, 0.1, 10)
+            out.backward(g)
+            outs.append(out.detach().clone())
+            grads.append(h.grad.clone())
+    assert all(torch.equal(outs[0], o) for o in outs[1:])
+    assert all(torch.equal(grads[0], x) for x in grads[1:])
