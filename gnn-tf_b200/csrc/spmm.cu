@@ -769,6 +769,10 @@ int spmm_dispatch(const gnntf_csr_t* A, const float* B, int64_t ldb, Epilogue ep
         if (slots <= 8) return launch_cfg<4, 1, 8>(A, B, ldb, epi, st);
         if (slots <= 16) return launch_cfg<4, 1, 16>(A, B, ldb, epi, st);
         if (slots <= 32) return launch_cfg<4, 1, 32>(A, B, ldb, epi, st);
+        // wider rows: 128-float tiles over grid.y with the one-slot mapping (8-deep gather batches);
+        // GNNTF_SPMM_WIDE=0 selects the multi-slot mappings instead (A/B)
+        static const int wide_tiles = env_int("GNNTF_SPMM_WIDE", 1);
+        if (wide_tiles) return launch_cfg<4, 1, 32>(A, B, ldb, epi, st);
         if (slots <= 64) return launch_cfg<4, 2, 32>(A, B, ldb, epi, st);
         return launch_cfg<4, 4, 32>(A, B, ldb, epi, st);  // tiles of 512 floats over grid.y
     }

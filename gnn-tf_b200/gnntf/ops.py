@@ -79,7 +79,9 @@ class _SpMM(torch.autograd.Function):
     @staticmethod
     def forward(ctx, adj, H):
         ctx.adj = adj
-        return _perm_out(adj, spmm_raw(adj.struct(H.shape[1]), adj.base.n, _perm_in(adj, H)))
+        Hp, F = _pad4(_perm_in(adj, H)) if H.shape[1] > 8 else (_perm_in(adj, H), H.shape[1])
+        out = _perm_out(adj, spmm_raw(adj.struct(Hp.shape[1]), adj.base.n, Hp))
+        return out if out.shape[1] == F else out[:, :F].contiguous()
 
     @staticmethod
     def backward(ctx, g):
@@ -87,7 +89,9 @@ class _SpMM(torch.autograd.Function):
         if not ctx.needs_input_grad[1]:
             return None, None  # e.g. the constant feature matrix of the first GCN layer
         g = _perm_in(adj, _dense(g))
-        return None, _perm_out(adj, spmm_raw(adj.struct_T(g.shape[1]), adj.base.n, g))
+        gp, F = _pad4(g) if g.shape[1] > 8 else (g, g.shape[1])
+        out = _perm_out(adj, spmm_raw(adj.struct_T(gp.shape[1]), adj.base.n, gp))
+        return None, (out if out.shape[1] == F else out[:, :F].contiguous())
 
 
 def sparse_dense_matmul(adj, H):
