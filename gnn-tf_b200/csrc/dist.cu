@@ -25,25 +25,52 @@ __global__ void halo_pack_kernel(const float* __restrict__ H, int64_t ld, const 
     }
 }
 
-// Fused pack + send: one warp per row; the destination is a peer GPU's halo buffer (NVLink stores).
-template <int VEC>
+// Fused pack + send: the destination is a peer GPU's halo buffer (NVLink stores).  G lanes own a
+// row (G sized to the row width), a warp runs 32/G rows side by side and every group keeps U rows
+// in flight (index loads, then all row loads, then all remote stores): the first version — one warp
+// per row, one row at a time — was latency-bound at 233 GB/s (profiles/r1, N=8 phase timing).
+template <int VEC, int G, int U>
 __global__ void halo_push_kernel(const float* __restrict__ H, int64_t ld, const int32_t* __restrict__ send_idx,
                                  const int64_t* __restrict__ send_off, float* const* __restrict__ peer_base,
                                  const int64_t* __restrict__ peer_row0, int n_peers, int64_t n_send,
                                  int64_t rotate, int64_t ldo, int F) {
+    constexpr int RPW = 32 / G;
     const int lane = threadIdx.x & 31;
-    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-    for (int64_t k = warp; k < n_send; k += nwarps) {
-        // every rank starts with a different destination, so at any moment each receiver is the
-        // target of (about) one sender instead of all of them
-        int64_t i = k + rotate;
-        if (i >= n_send) i -= n_send;
-        int d = 0;
-        while (d + 1 < n_peers && i >= send_off[d + 1]) ++d;   // n_peers <= 8: linear scan
-        const float* src = H + (int64_t)__ldg(send_idx + i) * ld;
-        float* dst = peer_base[d] + (peer_row0[d] + (i - send_off[d])) * ldo;
-        for (int f = lane * VEC; f < F; f += 32 * VEC) Vec<VEC>::gather(src + f).store(dst + f);
+    const int gl = lane % G;
+    const int64_t group = (((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5) * RPW + lane / G;
+    const int64_t n_groups = (((int64_t)gridDim.x * blockDim.x) >> 5) * RPW;
+    for (int64_t k0 = group; k0 < n_send; k0 += n_groups * U) {
+        const float* src[U];
+        float* dst[U];
+        bool ok[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int64_t k = k0 + (int64_t)u * n_groups;
+            ok[u] = k < n_send;
+            // every rank starts with a different destination, so at any moment each receiver is
+            // the target of (about) one sender instead of all of them
+            int64_t i = ok[u] ? k + rotate : 0;
+            if (i >= n_send) i -= n_send;
+            int d = 0;
+            while (d + 1 < n_peers && i >= send_off[d + 1]) ++d;   // n_peers <= 8: linear scan
+            src[u] = H + (int64_t)__ldg(send_idx + i) * ld;
+            dst[u] = ok[u] ? peer_base[d] + (peer_row0[d] + (i - send_off[d])) * ldo : nullptr;
+        }
+        if (F <= G * VEC) {  // one slot per lane: all U loads first, then all U stores
+            Vec<VEC> x[U];
+            const bool mine = gl * VEC < F;
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+                if (ok[u] && mine) x[u] = Vec<VEC>::gather(src[u] + gl * VEC);
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+                if (ok[u] && mine) x[u].store(dst[u] + gl * VEC);
+        } else {
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+                if (ok[u])
+                    for (int f = gl * VEC; f < F; f += G * VEC) Vec<VEC>::gather(src[u] + f).store(dst[u] + f);
+        }
     }
 }
 
@@ -80,12 +107,21 @@ extern "C" int gnntf_halo_push_f32(const float* H, int64_t ld, const int32_t* se
     static const int max_ctas = [] { const char* e = getenv("GNNTF_PUSH_CTAS"); return e ? std::max(1, atoi(e)) : kNumSMs; }();
     const int grid = (int)std::min<int64_t>(ceil_div(n_send, 8), (int64_t)max_ctas);
     const bool v4 = (F % 4 == 0) && (ld % 4 == 0) && (ldo % 4 == 0) && (reinterpret_cast<uintptr_t>(H) & 15u) == 0;
-    if (v4)
-        halo_push_kernel<4><<<grid, 256, 0, (cudaStream_t)stream>>>(H, ld, send_idx, send_off, peer_base, peer_row0,
-                                                                     n_peers, n_send, rotate, ldo, (int)F);
-    else
-        halo_push_kernel<1><<<grid, 256, 0, (cudaStream_t)stream>>>(H, ld, send_idx, send_off, peer_base, peer_row0,
-                                                                     n_peers, n_send, rotate, ldo, (int)F);
+    cudaStream_t st = (cudaStream_t)stream;
+#define GNNTF_PUSH(VEC, G)                                                                                     \
+    halo_push_kernel<VEC, G, 4><<<grid, 256, 0, st>>>(H, ld, send_idx, send_off, peer_base, peer_row0, n_peers, \
+                                                      n_send, rotate, ldo, (int)F)
+    if (v4) {
+        if (F <= 16) GNNTF_PUSH(4, 4);
+        else if (F <= 32) GNNTF_PUSH(4, 8);
+        else if (F <= 64) GNNTF_PUSH(4, 16);
+        else GNNTF_PUSH(4, 32);
+    } else {
+        if (F <= 8) GNNTF_PUSH(1, 8);
+        else if (F <= 16) GNNTF_PUSH(1, 16);
+        else GNNTF_PUSH(1, 32);
+    }
+#undef GNNTF_PUSH
     GNNTF_LAUNCH_CHECK();
     return GNNTF_OK;
 }
