@@ -196,10 +196,6 @@ def exchange_halo(plan: ShardPlan, send_buf, halo_out, group=None, async_op=Fals
                                   input_split_sizes=plan.send_counts, group=group, async_op=async_op)
 
 
-def p_world_gt1(world):
-    return world > 1 and torch.cuda.is_available()
-
-
 class _SharedMatrix:
     """fp32 [rows, cols] device matrix allocated through gnntf_ipc_alloc so that peers can map it
     (CUDA IPC) and store halo rows into it directly; exposed to torch without a copy."""
@@ -252,7 +248,7 @@ class ShardedPropagator:
         self.nat = nat
         self.group, self.F = group, int(F)
         self._exchange = exchange  # test hook: single-process emulation of the all-to-all
-        self.comm_stream = torch.cuda.Stream(priority=-1) if p_world_gt1(world) else None
+        self.comm_stream = torch.cuda.Stream(priority=-1) if (world > 1 and torch.cuda.is_available()) else None
         csr = A.csr
         self.plan = p = plan if plan is not None else build_shard_plan(csr.row_ptr, csr.col_idx, A.val, rank, world, group)
         self.lo, self.hi, self.n_local, self.n_halo = p.lo, p.hi, p.n_local, p.n_halo

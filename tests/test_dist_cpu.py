@@ -126,3 +126,37 @@ def test_split_by_column_preserves_entries_and_order():
             assert torch.equal(h_col[int(h_rp[i]):int(h_rp[i + 1])], c[~own]) and torch.equal(h_val[int(h_rp[i]):int(h_rp[i + 1])], v[~own])
         else:
             assert r not in hmap
+
+
+def test_grid_and_column_helpers():
+    sys.path.insert(0, os.path.join(ROOT, "gnn-tf_b200"))
+    from gnntf import dist as gdist
+    assert gdist.choose_grid(1, 100) == (1, 1) and gdist.choose_grid(2, 100) == (2, 1)
+    assert gdist.choose_grid(4, 100) == (4, 1) and gdist.choose_grid(8, 100) == (4, 2)
+    assert gdist.choose_grid(8, 47) == (8, 1)            # too narrow to split the columns
+    for F, C in ((100, 2), (100, 4), (47, 2), (128, 8), (7, 2)):
+        ranges = [gdist.column_range(F, C, c) for c in range(C)]
+        assert ranges[0][0] == 0 and ranges[-1][1] == F
+        assert all(a[1] == b[0] for a, b in zip(ranges, ranges[1:]))          # contiguous cover
+        assert all((lo % 4 == 0) for lo, _ in ranges)                          # 16-byte aligned starts
+
+
+def _grid_worker(rank, world, port, out_dir):
+    sys.path.insert(0, os.path.join(ROOT, "gnn-tf_b200"))
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from gnntf import dist as gdist
+        grid = gdist.Grid2D(rank, world, 2, 2)
+        assert (grid.r, grid.c) == (rank // 2, rank % 2)
+        t = torch.tensor([float(rank)])
+        dist.all_reduce(t, group=grid.row_group)             # sums over the ranks of my column group
+        assert t.item() == float(grid.c + (2 + grid.c))      # ranks c and 2+c
+        np.save(os.path.join(out_dir, f"grid_{rank}.npy"), np.array([grid.r, grid.c]))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_grid2d_process_groups_gloo(tmp_path):
+    mp.spawn(_grid_worker, args=(4, _free_port(), str(tmp_path)), nprocs=4, join=True)
+    assert sorted(tuple(np.load(tmp_path / f"grid_{r}.npy")) for r in range(4)) == [(0, 0), (0, 1), (1, 0), (1, 1)]

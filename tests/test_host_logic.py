@@ -107,3 +107,11 @@ def test_synthetic_shapes():
     assert (r[:, 0] - r[:, 1]).abs().float().median() > 20 * (edges[:, 0] - edges[:, 1]).abs().float().median()
     nr, er = synthetic.rmat_edges(12, 50000, seed=1)
     assert nr == 4096 and er.shape == (50000, 2) and int(er.max()) < nr
+
+
+def test_reorder_rank_uniformisation_is_a_permutation():
+    from gnntf.reorder import _uniformize
+    theta = torch.tensor([3.0, 0.1, 6.0, 2.0, 0.05])
+    ranks, order = _uniformize(theta)
+    assert order.tolist() == [4, 1, 3, 0, 2]
+    assert torch.allclose(ranks, torch.tensor([3, 1, 4, 2, 0], dtype=torch.float32) * (2 * np.pi / 5))
