@@ -9,13 +9,15 @@
 // <= 32) own one sparse row; lane `gl` of the group owns slots gl, gl+GROUP, ... (NSLOT of them),
 // so the lanes of a group read one contiguous GROUP*VEC*4-byte span of each gathered row.  A warp
 // therefore runs 32/GROUP sparse rows at once.  The group's lanes fetch GROUP (col,val) pairs with
-// one coalesced streaming load each and broadcast them with width-GROUP shuffles; the gathers of
-// UNROLL consecutive entries are issued back to back before the FMAs (memory-level parallelism).
+// one coalesced streaming load each and broadcast them through a small per-warp shared-memory
+// buffer; the gathers of UNROLL consecutive entries are issued back to back before the FMAs
+// (memory-level parallelism).  Rows wider than 128 floats run as 128-float tiles over grid.y.
 //
 // Accumulation order inside a row is CSR slot order = COO storage order (the builder's sort is
 // stable), i.e. the order TF's CPU kernel uses.  Rows longer than A->long_threshold are skipped
-// here and run as fixed-size pieces on separate warps (spmm_chunk_kernel), whose partial sums are
-// combined in piece order by spmm_long_reduce_kernel: deterministic, no float atomics.
+// by the row warps and run as fixed-size pieces on other warps of the same grid (process_piece),
+// whose partial sums are combined in piece order by spmm_long_reduce_kernel: deterministic, no
+// float atomics.
 #include <algorithm>
 #include <cstdlib>
 #include <type_traits>
@@ -23,7 +25,6 @@
 #include "spmm.cuh"
 
 namespace gnntf {
-
 
 template <int VEC>
 __device__ __forceinline__ void apply_epilogue(const Epilogue& e, int64_t row, int f, Vec<VEC> acc) {
@@ -197,8 +198,8 @@ __device__ __forceinline__ void process_piece(const int* __restrict__ row_ptr, c
 // version launched 306 k CTAs on the products shape and ran at 47 % achieved occupancy);
 // grid.y walks feature tiles of GROUP*NSLOT*VEC floats.
 // A gather address costs one mad.wide.u32 (the first profile showed 28 executed instructions per
-// entry, most of them 64-bit address arithmetic, per-entry predicates and register zeroing); full
-// batches of UNROLL entries run predicate-free.
+// entry, most of them 64-bit address arithmetic, per-entry predicates and register zeroing); every
+// batch of UNROLL entries runs predicate-free (short rows are padded, see the loop).
 // ---------------------------------------------------------------------------------------------
 
 // Address of a gathered row piece in ONE instruction: column ids are non-negative int32 and the
