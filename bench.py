@@ -162,10 +162,12 @@ def load_oracle_c():
     lib.oracle_normalize_sym_f32.argtypes = [P, P, ctypes.c_int64, ctypes.c_int64, P, P]
     lib.oracle_spmm_coo_f32.argtypes = [P, P, ctypes.c_int64, ctypes.c_int64, P, ctypes.c_int64, P]
     lib.oracle_teleport_f32.argtypes = [P, P, ctypes.c_int64, ctypes.c_float, P]
+    lib.oracle_appnp_step_csr_omp_f32.argtypes = [P, P, P, P, P, ctypes.c_int64, ctypes.c_float, ctypes.c_int64,
+                                                  ctypes.c_int64, P]
     return lib
 
 
-def cpu_arm(n, edges_cpu, F, seconds_per_step, steps, warmup):
+def cpu_arm(n, edges_cpu, F, seconds_per_step, steps, warmup, multi_thread_context=True):
     """Times the oracle's restatement of filter.py:19-21 (COO-order SpMM loop as in TF-CPU's
     SparseTensorDenseMatMul functor + teleport) on a bounded prefix of the COO list."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
@@ -199,9 +201,25 @@ def cpu_arm(n, edges_cpu, F, seconds_per_step, steps, warmup):
     t = float(np.mean(times))
     value = sample * F / t
     omp = int(os.environ.get("OMP_NUM_THREADS", os.cpu_count() or 1))
+    # context: the same step as a row-parallel CSR SpMM on every host thread (not what TF-CPU does)
+    mt = None
+    if multi_thread_context:
+        row_ptr, col_idx, coo_pos, _ = oracle.csr_from_coo(idx, n)
+        csr_val = np.ascontiguousarray(norm[coo_pos])
+        del coo_pos
+        rows_cap = int(n * min(1.0, max(0.02, seconds_per_step * value * 4 / (nnz * F))))  # bounded: a few seconds
+        lib.oracle_appnp_step_csr_omp_f32(row_ptr.ctypes.data, col_idx.ctypes.data, csr_val.ctypes.data, H.ctypes.data,
+                                          H.ctypes.data, F, ctypes.c_float(ALPHA), 0, min(rows_cap, n), out.ctypes.data)
+        t0 = time.perf_counter()
+        lib.oracle_appnp_step_csr_omp_f32(row_ptr.ctypes.data, col_idx.ctypes.data, csr_val.ctypes.data, H.ctypes.data,
+                                          H.ctypes.data, F, ctypes.c_float(ALPHA), 0, min(rows_cap, n), out.ctypes.data)
+        dt = time.perf_counter() - t0
+        done = int(row_ptr[min(rows_cap, n)])
+        mt = {"mt_value": done * F / dt, "mt_cores": omp, "mt_sample": f"rows 0..{min(rows_cap, n)} ({done} entries), 1 timed rep",
+              "mt_kind": "row-parallel CSR SpMM + fused teleport on all OpenMP threads (context only: TF-CPU's kernel for this op is a single-threaded COO loop)"}
     desc = (f"{sample} of {nnz} COO entries (prefix, storage order) x F={F}: one PPR iteration's SpMM + teleport, "
             f"{len(times)} timed reps; SpMM loop single-threaded as in TF-CPU, element-wise pass on {omp} OpenMP threads")
-    return value, t, sample, desc, omp
+    return value, t, sample, desc, omp, mt
 
 
 # ----------------------------------------------------------------------------------------------
@@ -356,9 +374,10 @@ def gpu_arm(args):
     # ---- CPU baseline (rank 0, N=1 only) ----------------------------------------------------
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         t0 = time.time()
-        v, t, sample, desc, omp = cpu_arm(n, edges.cpu().numpy(), F, seconds_per_step=6.0, steps=2, warmup=1)
+        v, t, sample, desc, omp, mt = cpu_arm(n, edges.cpu().numpy(), F, seconds_per_step=6.0, steps=2, warmup=1)
         result["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": omp, "kind": "port", "sample": desc,
                                   "host_cpus": os.cpu_count(), "wall_s": time.time() - t0}
+        result["cpu_baseline"].update(mt or {})
     if rank == 0:
         os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
         emit_json(result)
@@ -374,15 +393,15 @@ def reference_arm(args):
     n, edges, F = make_workload(args, "cpu")
     nnz = 2 * edges.shape[0]
     budget = 150.0 / max(1, args.steps + args.warmup)
-    v, t, sample, desc, omp = cpu_arm(n, edges.numpy(), F, seconds_per_step=min(20.0, budget), steps=args.steps,
-                                      warmup=args.warmup)
+    v, t, sample, desc, omp, mt = cpu_arm(n, edges.numpy(), F, seconds_per_step=min(20.0, budget), steps=args.steps,
+                                          warmup=args.warmup)
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": K_ITER * nnz * F / v * 1e3, "ms_per_step_note": "K=10 propagation time extrapolated from the sampled rate",
             "sample_ms": t * 1e3, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": config_dict(args, n, edges.shape[0], nnz, F),
-            "cpu_baseline": {"value": v, "unit": UNIT, "cores": omp, "kind": "port", "sample": desc,
-                             "host_cpus": os.cpu_count()},
+            "cpu_baseline": dict({"value": v, "unit": UNIT, "cores": omp, "kind": "port", "sample": desc,
+                                  "host_cpus": os.cpu_count()}, **(mt or {})),
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "note": "the reference (TensorFlow) cannot be installed in this image; this is the oracle's C port of its "
                     "CPU path (COO-order single-threaded SpMM loop + teleport), timed on a bounded sample"}

@@ -88,3 +88,26 @@ void oracle_appnp_propagate_f32(const int64_t* idx, const float* raw_val, int64_
         H = H_out;
     }
 }
+
+/* Context only, NOT what the reference executes: one PPR iteration as a row-parallel CSR SpMM with
+ * the teleport fused, on all OpenMP threads — the best a CPU port could reasonably do with the
+ * host's cores.  bench.py reports it beside the faithful single-threaded COO loop above
+ * (cpu_baseline.mt_value) so the GPU/CPU ratio is not only a ratio against one core.
+ * row_ptr int64 [n+1], col int32 [nnz], val fp32 [nnz] (normalised), rows [r_lo, r_hi). */
+void oracle_appnp_step_csr_omp_f32(const int64_t* row_ptr, const int32_t* col, const float* val,
+                                   const float* H, const float* H0, int64_t F, float a,
+                                   int64_t r_lo, int64_t r_hi, float* out) {
+    const float one_minus_a = (float)(1 - (double)a);
+#pragma omp parallel for schedule(dynamic, 256)
+    for (int64_t r = r_lo; r < r_hi; ++r) {
+        float* __restrict__ o = out + r * F;
+        for (int64_t f = 0; f < F; ++f) o[f] = 0.0f;
+        for (int64_t p = row_ptr[r]; p < row_ptr[r + 1]; ++p) {
+            const float v = val[p];
+            const float* __restrict__ h = H + (int64_t)col[p] * F;
+            for (int64_t f = 0; f < F; ++f) o[f] += v * h[f];
+        }
+        const float* __restrict__ h0 = H0 + r * F;
+        for (int64_t f = 0; f < F; ++f) o[f] = o[f] * one_minus_a + h0[f] * a;
+    }
+}

@@ -165,3 +165,22 @@ def test_c_oracle_matches_numpy_oracle(oracle_c):
     oracle.assert_close(out, expect, rtol=1e-6, what="C oracle vs NumPy oracle")
     _, nv, D = oracle.get_adjacency(idx, val, n)
     np.testing.assert_allclose(scratch[:nnz], nv, rtol=2e-7)
+
+
+def test_c_oracle_multithreaded_csr_step_matches_numpy_oracle(oracle_c):
+    """The row-parallel CSR step bench.py reports as multi-threaded CPU context."""
+    rng = np.random.default_rng(4)
+    n, e, F, a = 2000, 25000, 33, 0.1
+    idx, val, _ = oracle.graph2adj_arrays(rng.integers(0, n, (e, 2)), rng.random(e).astype(np.float32) + 0.5, n)
+    _, nv, _ = oracle.get_adjacency(idx, val, n)
+    row_ptr, col, pos, _ = oracle.csr_from_coo(idx, n)
+    csr_val = np.ascontiguousarray(nv[pos])
+    H = rng.standard_normal((n, F)).astype(np.float32)
+    H0 = rng.standard_normal((n, F)).astype(np.float32)
+    out = np.zeros((n, F), np.float32)
+    P = ctypes.c_void_p
+    oracle_c.oracle_appnp_step_csr_omp_f32.argtypes = [P, P, P, P, P, ctypes.c_int64, ctypes.c_float, ctypes.c_int64,
+                                                       ctypes.c_int64, P]
+    oracle_c.oracle_appnp_step_csr_omp_f32(row_ptr.ctypes.data, col.ctypes.data, csr_val.ctypes.data, H.ctypes.data,
+                                           H0.ctypes.data, F, ctypes.c_float(a), 0, n, out.ctypes.data)
+    oracle.assert_close(out, oracle.ppr_iteration(idx, nv, H, H0, a), what="CSR/OpenMP step")
