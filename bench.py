@@ -336,7 +336,7 @@ def gpu_arm(args):
                                "median": float(per_step_ms.median().item())},
             "clocks": clocks, "gpu_launches": launches_per_step * args.steps,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                         "traffic": measured_traffic(args, F), "peak_source": peak_src, "frac_of_nominal_8TBs": achieved / 8000.0,
+                         "traffic": measured_traffic(args, F) if world == 1 else None, "peak_source": peak_src, "frac_of_nominal_8TBs": achieved / 8000.0,
                          "kernel": "fused APPNP step (spmm_rows_kernel + long-row pieces/reduce)",
                          "algorithmic_bytes_per_launch": bstep,
                          "avg_launch_ms": ms_per_step / K_ITER,
