@@ -2,7 +2,7 @@
 hand-written sm_100a kernels (``libgnntf_b200.so``) behind a C-ABI.  See DESIGN.md.
 
 Exports mirror ``gnntf/__init__.py:1-2`` of the reference for the path in scope."""
-from .graph_manipulation import adj2graph, create_nx_graph, edges2adj, graph2adj, graph2indices
+from .graph_manipulation import adj2graph, create_nx_graph, csr2adj, edges2adj, graph2adj, graph2indices
 from .measures import acc, set_seed
 from .nn import (Activation, Dense, Dropout, Layer, Layered, Predictor, Trainable, VariableGenerator,
                  WrappedVariable)

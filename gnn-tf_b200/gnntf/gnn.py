@@ -160,8 +160,14 @@ class GCNLayer(Layer):
         return (gcn.top_shape()[0], outputs)
 
     def __forward__(self, gcn, features):
-        aggregated = ops.sparse_dense_matmul(gcn.get_adjacency(self.graph_dropout), features)   # gcn.py:88
-        return gcn.dropout(self.activation(aggregated @ self.W + self.b), self.dropout)         # gcn.py:89
+        adjacency = gcn.get_adjacency(self.graph_dropout)
+        if self.W.shape[1] < features.shape[1]:
+            # (Â·X)·W == Â·(X·W): when the layer narrows, propagate at the OUTPUT width (PubMed layer 1:
+            # SpMM at 64 columns instead of 500).  Same value up to fp32 rounding.
+            transformed = ops.sparse_dense_matmul(adjacency, features @ self.W)
+        else:
+            transformed = ops.sparse_dense_matmul(adjacency, features) @ self.W                  # gcn.py:88
+        return gcn.dropout(self.activation(transformed + self.b), self.dropout)                  # gcn.py:89
 
 
 class GCN(GNN):

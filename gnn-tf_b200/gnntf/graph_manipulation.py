@@ -60,6 +60,21 @@ def edges2adj(edges, weights=None, num_nodes=None, directed=False):
     return SparseAdjacency(edges, weights, num_nodes, directed)
 
 
+def csr2adj(indptr, indices, data=None, directed=True):
+    """Adjacency from CSR arrays (the ``.npz`` format of the reference's loaders,
+    experiments/experiment_setup.py:273-282: ``adj_indptr``/``adj_indices``/``adj_data``).  The CSR
+    rows are expanded to the edge list ``[[row, col], ...]`` in CSR order, then handled exactly like
+    ``graph2adj``'s list.  ``directed=True`` (default) takes the matrix as stored; ``False`` appends the
+    reversed list as ``graph2adj`` does."""
+    indptr = np.asarray(indptr, dtype=np.int64)
+    indices = np.asarray(indices, dtype=np.int64)
+    n = indptr.shape[0] - 1
+    rows = np.repeat(np.arange(n, dtype=np.int64), np.diff(indptr))
+    edges = np.stack([rows, indices], axis=1)
+    weights = None if data is None else np.asarray(data, dtype=np.float32)
+    return edges2adj(edges, weights, n, directed)
+
+
 def graph2adj(G, directed=False):
     """graph_manipulation.py:24-31.  Returns an object with the SparseTensor fields the reference
     exposes (``indices`` int64 [nnz,2] in the reference order, ``values``, ``dense_shape``/``shape``)."""

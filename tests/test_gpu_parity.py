@@ -633,3 +633,15 @@ def test_propagation_is_bitwise_deterministic():
             grads.append(h.grad.clone())
     assert all(torch.equal(outs[0], o) for o in outs[1:])
     assert all(torch.equal(grads[0], x) for x in grads[1:])
+
+
+def test_csr2adj_matches_edges2adj():
+    import scipy.sparse as sp
+    gnntf = _gnntf()
+    rng = np.random.default_rng(1)
+    M = sp.random(300, 300, density=0.02, format="csr", random_state=3, dtype=np.float32)
+    adj = gnntf.csr2adj(M.indptr, M.indices, M.data)
+    assert adj.directed and adj.csr.nnz == M.nnz
+    H = rng.standard_normal((300, 12)).astype(np.float32)
+    got = _np(gnntf.sparse_dense_matmul(adj.normalized("none"), torch.from_numpy(H).cuda()))
+    oracle.assert_close(got, M @ H, what="csr2adj SpMM")
