@@ -236,11 +236,11 @@ class _EventWork:
 class ShardedPropagator:
     """APPNP K-step propagation of one shard on one GPU (see module docstring).
 
-    ``halves=2`` (default when world > 1) runs the propagation as two independent chains over the
-    two halves of the feature columns (columns propagate independently through
-    H <- (1-a)·Â·H + a·H0), software-pipelined so that the halo exchange of one half for step k+1
-    is in flight while the other half computes step k.  Costs a second pass over the CSR and
-    narrower gathers (~1.2x compute), hides most of the exchange."""
+    ``push`` (default): halo rows travel by the fused pack+send kernel over NVLink peer memory
+    (``gnntf_halo_push_f32``); if the peers' buffers cannot be mapped every rank falls back to the
+    NCCL all-to-all.  ``halves=2`` runs two independent chains over the two halves of the feature
+    columns, software-pipelined so one half's exchange is in flight while the other half computes —
+    kept for experiments, measured slower than the default."""
 
     def __init__(self, adj, A, F, rank, world, group=None, plan=None, exchange=None, halves=None, push=True):
         from . import _native as nat
@@ -274,8 +274,7 @@ class ShardedPropagator:
                 bufs = [m.tensor for m in mats]
             else:
                 bufs = [torch.zeros((n_ext, w), dtype=torch.float32, device=dev) for _ in range(2)]
-            self.parts.append(dict(F=w, col0=col0, buf=bufs,
-                                   send=torch.empty((n_send, w), dtype=torch.float32, device=dev),
+            self.parts.append(dict(F=w, col0=col0, buf=bufs, send=None, n_send=n_send,   # send buffer: NCCL path only
                                    H0=torch.empty((self.n_local, w), dtype=torch.float32, device=dev), work=None))
             col0 += w
         if self.push:
@@ -289,8 +288,16 @@ class ShardedPropagator:
             dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.group)
             if flag.item() < 1.0:
                 self.push = False  # the shared buffers are ordinary device memory for the NCCL path
+        if not self.push:
+            for part in self.parts:
+                self._send_buffer(part)
         # single-part aliases (tests and the emulation hook address them directly)
         self.buf, self.send_buf, self.H0 = self.parts[0]["buf"], self.parts[0]["send"], self.parts[0]["H0"]
+
+    def _send_buffer(self, part):
+        if part["send"] is None:
+            part["send"] = torch.empty((part["n_send"], part["F"]), dtype=torch.float32, device=part["H0"].device)
+        return part["send"]
 
     def _map_peers(self):
         """Exchange IPC handles and halo layouts inside the row group and build, per part and per
@@ -360,16 +367,17 @@ class ShardedPropagator:
                                                     n_send, self._rotate, F, F, nat.stream_ptr()), "halo_push")
                 part["work"] = dist.all_reduce(self._flag, group=self.group, async_op=True)
                 return
-            if part["send"].shape[0] > 0:
-                nat.check(L.gnntf_halo_pack_f32(nat.ptr(src), F, nat.ptr(p.send_idx), part["send"].shape[0],
-                                                nat.ptr(part["send"]), F, F, nat.stream_ptr()), "halo_pack")
+            send = self._send_buffer(part)
+            if send.shape[0] > 0:
+                nat.check(L.gnntf_halo_pack_f32(nat.ptr(src), F, nat.ptr(p.send_idx), send.shape[0],
+                                                nat.ptr(send), F, F, nat.stream_ptr()), "halo_pack")
             if self._exchange is not None:
-                self._exchange(self, part["send"], src[self.n_local:])
+                self._exchange(self, send, src[self.n_local:])
                 done = torch.cuda.Event()
                 done.record()
                 part["work"] = _EventWork(done)
             else:
-                part["work"] = exchange_halo(p, part["send"], src[self.n_local:], self.group, async_op=True)
+                part["work"] = exchange_halo(p, send, src[self.n_local:], self.group, async_op=True)
 
     def _compute(self, part, src, dst, alpha):
         nat, L = self.nat, self.nat.lib()

@@ -63,10 +63,12 @@ if R > 1:
         push()
         dist.all_reduce(prop._flag, group=grid.row_group)
 
+    send = prop._send_buffer(part)
+
     def pack_a2a():
-        nat.check(L.gnntf_halo_pack_f32(nat.ptr(src), Fc, nat.ptr(p.send_idx), part["send"].shape[0], nat.ptr(part["send"]),
+        nat.check(L.gnntf_halo_pack_f32(nat.ptr(src), Fc, nat.ptr(p.send_idx), send.shape[0], nat.ptr(send),
                                         Fc, Fc, nat.stream_ptr()))
-        gdist.exchange_halo(p, part["send"], src[prop.n_local:], grid.row_group, async_op=False)
+        gdist.exchange_halo(p, send, src[prop.n_local:], grid.row_group, async_op=False)
     res.update(push=t(push), push_plus_barrier=t(push_barrier), barrier=t(lambda: dist.all_reduce(prop._flag, group=grid.row_group)),
                nccl_pack_a2a=t(pack_a2a))
 
