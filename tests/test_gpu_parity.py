@@ -645,3 +645,36 @@ def test_csr2adj_matches_edges2adj():
     H = rng.standard_normal((300, 12)).astype(np.float32)
     got = _np(gnntf.sparse_dense_matmul(adj.normalized("none"), torch.from_numpy(H).cuda()))
     oracle.assert_close(got, M @ H, what="csr2adj SpMM")
+
+
+def test_arrange_sweep_kernel_vs_numpy():
+    """gnntf_arrange_sweep_f32 against the same formula in NumPy (fp64): weighted circular mean of the
+    neighbours' positions with weights 1/(|offset| + eps); isolated nodes keep their position."""
+    gnntf = _gnntf()
+    nat = gnntf._native
+    n, e = 700, 5000
+    edges, _ = _random_edges(n, e, seed=31)
+    edges = edges[edges[:, 0] < n - 5]
+    edges = edges[edges[:, 1] < n - 5]                      # the last nodes are isolated
+    adj = gnntf.edges2adj(edges, None, n)
+    rng = np.random.default_rng(2)
+    theta = (rng.random(n) * 2 * np.pi).astype(np.float32)
+    eps = 0.05
+    out = torch.empty(n, device="cuda")
+    nat.check(nat.lib().gnntf_arrange_sweep_f32(nat.ptr(adj.csr.row_ptr), nat.ptr(adj.csr.col_idx),
+                                                nat.ptr(torch.from_numpy(theta).cuda()), eps, nat.ptr(out), n,
+                                                nat.stream_ptr()))
+    rp, col = _np(adj.csr.row_ptr), _np(adj.csr.col_idx)
+    t64 = theta.astype(np.float64)
+    expect = t64.copy()
+    for i in range(n):
+        nb = col[rp[i]:rp[i + 1]]
+        if nb.size:
+            d = t64[nb] - t64[i]
+            d -= 2 * np.pi * np.rint(d / (2 * np.pi))
+            w = 1.0 / (np.abs(d) + eps)
+            expect[i] = (t64[i] + (w * d).sum() / w.sum()) % (2 * np.pi)
+    diff = np.abs(_np(out).astype(np.float64) - expect)
+    diff = np.minimum(diff, 2 * np.pi - diff)               # compare on the circle
+    assert diff.max() < 2e-5, diff.max()
+    assert np.array_equal(_np(out)[n - 5:], theta[n - 5:])
