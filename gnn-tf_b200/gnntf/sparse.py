@@ -12,9 +12,12 @@ import torch
 
 from . import _native as nat
 
-# rows longer than this many entries are split into pieces of `CHUNK` entries (see spmm.cu)
-LONG_THRESHOLD = 256
-CHUNK = 256
+import os
+
+# rows longer than this many entries are split into pieces of `CHUNK` entries (see spmm.cu);
+# GNNTF_LONG_THRESHOLD / GNNTF_CHUNK override for A/B measurements
+LONG_THRESHOLD = int(os.environ.get("GNNTF_LONG_THRESHOLD", 256))
+CHUNK = int(os.environ.get("GNNTF_CHUNK", 256))
 
 
 def _require_cuda():
