@@ -277,7 +277,9 @@ def gpu_arm(args):
         H0_local = (H0 if adj.perm is None else H0.index_select(0, adj.perm))[prop.lo:prop.hi, c0:c1].contiguous()
         run = lambda: prop.propagate(H0_local, ALPHA, K_ITER)  # noqa: E731
         launches_per_step = prop.launches_per_propagation(K_ITER)
-        sharding = (f"{R} row groups (contiguous node ranges balanced by nnz; halo rows by NCCL all-to-all inside a column "
+        how = ("fused pack+send over NVLink peer memory + one-element NCCL all-reduce as barrier" if prop.push
+               else "pack kernel + NCCL all-to-all")
+        sharding = (f"{R} row groups (contiguous node ranges balanced by nnz; halo rows by {how}, inside a column "
                     f"group) x {C} feature-column groups (no communication)")
         del H0
     else:
