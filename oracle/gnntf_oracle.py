@@ -299,23 +299,44 @@ def csr_from_coo(indices, n, directed=False):
 # --------------------------------------------------------------------------------------
 
 RTOL = 1e-5
+# Elements smaller than FLOOR·‖y‖∞ are held to the absolute bound RTOL·FLOOR·‖y‖∞ (SURVEY.md §8c:
+# |x−y| ≤ 1e-5·max(|y|, 1e-3·‖y‖∞)).  An element-wise relative error is unbounded where the
+# expected value crosses zero.
+FLOOR = 1e-3
+
+# Every call appends {"what", "size", "max_abs_err_over_norm", "max_err_over_bound", "rtol",
+# "floor"}: tests/conftest.py writes the list to gpurun_out/parity_report.json at session end, so
+# the measured worst error of every parity test is on record.
+PARITY_LOG = []
 
 
-def assert_close(actual, expected, rtol=RTOL, what=""):
-    """|x−y| ≤ rtol·max(|y|, 0.1·‖y‖∞): 1e-5 relative, with a norm-wise floor for small elements
-    (they are held to 1e-6·‖y‖∞ absolute).  An elementwise relative error is unbounded where the
-    expected value crosses zero, and fp32 rounding noise is ~1e-7·‖y‖∞ per
-    accumulation: the fp32 oracle itself sits 1e-6·‖y‖∞ from its fp64 twin after K=10 steps."""
+def parity_stats(actual, expected, rtol=RTOL, floor=FLOOR):
     a = np.asarray(actual, dtype=np.float64)
     e = np.asarray(expected, dtype=np.float64)
-    assert a.shape == e.shape, f"{what}: shape {a.shape} vs {e.shape}"
     if e.size == 0:
-        return
-    floor = 0.1 * float(np.max(np.abs(e))) if e.size else 0.0
-    bound = rtol * np.maximum(np.abs(e), floor)
+        return dict(size=0, norm=0.0, max_abs_err_over_norm=0.0, max_err_over_bound=0.0, worst=None)
+    norm = float(np.max(np.abs(e)))
+    bound = rtol * np.maximum(np.abs(e), floor * norm)
     err = np.abs(a - e)
-    bad = err > bound
-    if bad.any():
-        i = np.unravel_index(np.argmax(err / np.maximum(bound, 1e-300)), e.shape)
-        raise AssertionError(f"{what}: {int(bad.sum())}/{e.size} outside rtol={rtol}; worst at {i}: "
-                             f"{a[i]!r} vs {e[i]!r}")
+    ratio = err / np.maximum(bound, 1e-300)
+    i = np.unravel_index(int(np.argmax(ratio)), e.shape)
+    return dict(size=int(e.size), norm=norm, max_abs_err_over_norm=float(err.max() / norm) if norm > 0 else float(err.max()),
+                max_err_over_bound=float(ratio[i]), worst=(tuple(int(x) for x in i), float(a[i]), float(e[i])),
+                n_bad=int((err > bound).sum()))
+
+
+def assert_close(actual, expected, rtol=RTOL, what="", floor=FLOOR):
+    """|x−y| ≤ rtol·max(|y|, floor·‖y‖∞): the north_star's 1e-5 relative with SURVEY.md §8c's
+    norm-wise floor (default 1e-3·‖y‖∞) for elements near zero.  A test that needs a larger floor
+    says so at the call site, with the measured worst error."""
+    a = np.asarray(actual)
+    e = np.asarray(expected)
+    assert a.shape == e.shape, f"{what}: shape {a.shape} vs {e.shape}"
+    st = parity_stats(a, e, rtol, floor)
+    PARITY_LOG.append(dict(what=what, size=st["size"], max_abs_err_over_norm=st["max_abs_err_over_norm"],
+                           max_err_over_bound=st["max_err_over_bound"], rtol=rtol, floor=floor))
+    if st["size"] and st["max_err_over_bound"] > 1.0:
+        i, av, ev = st["worst"]
+        raise AssertionError(f"{what}: {st['n_bad']}/{st['size']} outside rtol={rtol} (floor {floor}·‖y‖∞); worst at {i}: "
+                             f"{av!r} vs {ev!r} ({st['max_err_over_bound']:.2f}x the bound; max |err|/‖y‖∞ = "
+                             f"{st['max_abs_err_over_norm']:.3g})")

@@ -111,3 +111,67 @@ void oracle_appnp_step_csr_omp_f32(const int64_t* row_ptr, const int32_t* col, c
         for (int64_t f = 0; f < F; ++f) o[f] = o[f] * one_minus_a + h0[f] * a;
     }
 }
+
+/* Stable-by-row CSR view of a COO list, in O(nnz) (counting sort).  The reference never builds a
+ * CSR: tf.sparse.sparse_dense_matmul (filter.py:19) walks the COO entries in storage order, so each
+ * output row accumulates ITS entries in storage order.  A stable sort by row keeps exactly that
+ * order inside every row, hence a row-wise loop over this CSR performs the same fp32 operations on
+ * every output element as the sequential COO loop (oracle_spmm_coo_f32) — bit-identical results —
+ * while letting rows run on different threads.  This is what lets the tests and bench.py check
+ * full-size configs in seconds.  idx: int64 [nnz,2] (graph_manipulation.py:31 order);
+ * row_ptr int64 [n+1], col int32 [nnz], coo_pos int64 [nnz] (COO slot of each CSR slot). */
+void oracle_csr_from_coo(const int64_t* idx, int64_t nnz, int64_t n, int64_t* row_ptr, int32_t* col,
+                         int64_t* coo_pos) {
+    memset(row_ptr, 0, (size_t)(n + 1) * sizeof(int64_t));
+    for (int64_t i = 0; i < nnz; ++i) row_ptr[idx[2 * i] + 1] += 1;
+    for (int64_t r = 0; r < n; ++r) row_ptr[r + 1] += row_ptr[r];
+    int64_t* cursor = (int64_t*)malloc((size_t)(n > 0 ? n : 1) * sizeof(int64_t));
+    memcpy(cursor, row_ptr, (size_t)n * sizeof(int64_t));
+    for (int64_t i = 0; i < nnz; ++i) {
+        const int64_t p = cursor[idx[2 * i]]++;
+        col[p] = (int32_t)idx[2 * i + 1];
+        coo_pos[p] = i;
+    }
+    free(cursor);
+}
+
+/* out[p] = src[pos[p]] (values from COO order into CSR order). */
+void oracle_gather_f32(const float* src, const int64_t* pos, int64_t count, float* out) {
+#pragma omp parallel for schedule(static)
+    for (int64_t p = 0; p < count; ++p) out[p] = src[pos[p]];
+}
+
+/* Row-wise SpMM over the stable CSR (same per-element operation sequence as oracle_spmm_coo_f32,
+ * see oracle_csr_from_coo), rows on OpenMP threads.  filter.py:19 / gcn.py:88. */
+void oracle_spmm_csr_omp_f32(const int64_t* row_ptr, const int32_t* col, const float* val,
+                             const float* H, int64_t F, int64_t r_lo, int64_t r_hi, float* out) {
+#pragma omp parallel for schedule(dynamic, 256)
+    for (int64_t r = r_lo; r < r_hi; ++r) {
+        float* __restrict__ o = out + r * F;
+        for (int64_t f = 0; f < F; ++f) o[f] = 0.0f;
+        for (int64_t p = row_ptr[r]; p < row_ptr[r + 1]; ++p) {
+            const float v = val[p];
+            const float* __restrict__ h = H + (int64_t)col[p] * F;
+            for (int64_t f = 0; f < F; ++f) o[f] += v * h[f];
+        }
+    }
+}
+
+/* K PPRIteration layers (filter.py:17-22 under layered.py:52-55), eval mode, over the stable CSR:
+ * bit-identical to oracle_appnp_propagate_f32 on the same normalised values, but rows run on all
+ * OpenMP threads.  scratch: n*F floats.  The result ends in H_out. */
+void oracle_appnp_propagate_csr_omp_f32(const int64_t* row_ptr, const int32_t* col, const float* val,
+                                        int64_t n, const float* H0, int64_t F, float a, int K,
+                                        float* scratch, float* H_out) {
+    if (K == 0) {
+        memcpy(H_out, H0, (size_t)n * F * sizeof(float));
+        return;
+    }
+    const float* src = H0;
+    for (int k = 0; k < K; ++k) {
+        float* dst = ((K - 1 - k) % 2 == 0) ? H_out : scratch;
+        oracle_spmm_csr_omp_f32(row_ptr, col, val, src, F, 0, n, dst);
+        oracle_teleport_f32(dst, H0, n * F, a, dst);
+        src = dst;
+    }
+}

@@ -184,3 +184,51 @@ def test_c_oracle_multithreaded_csr_step_matches_numpy_oracle(oracle_c):
     oracle_c.oracle_appnp_step_csr_omp_f32(row_ptr.ctypes.data, col.ctypes.data, csr_val.ctypes.data, H.ctypes.data,
                                            H0.ctypes.data, F, ctypes.c_float(a), 0, n, out.ctypes.data)
     oracle.assert_close(out, oracle.ppr_iteration(idx, nv, H, H0, a), what="CSR/OpenMP step")
+
+
+# ------------------------------------------------------------------------------------------
+# The full-size checker (oracle/oracle_big.py): its CSR route must be the COO route, bit for bit
+# ------------------------------------------------------------------------------------------
+def _random_graph(n, e, seed, hub=False):
+    rng = np.random.default_rng(seed)
+    edges = rng.integers(0, n, size=(e, 2)).astype(np.int64)
+    if hub:  # a few rows far longer than the GPU's split threshold
+        edges[: e // 4, 0] = rng.integers(0, 3, size=e // 4)
+    w = (rng.random(e) + 0.25).astype(np.float32)
+    return edges, w
+
+
+def test_big_oracle_csr_is_the_stable_row_sort_of_the_coo_list():
+    import oracle_big
+    edges, w = _random_graph(300, 4000, 0, hub=True)
+    idx, val, _ = oracle.graph2adj_arrays(edges, w, 300)
+    row_ptr, col, coo_pos = oracle_big.csr_from_coo(idx, 300)
+    e_rp, e_col, e_pos, _ = oracle.csr_from_coo(idx, 300)
+    assert np.array_equal(row_ptr, e_rp) and np.array_equal(col, e_col) and np.array_equal(coo_pos, e_pos)
+
+
+@pytest.mark.parametrize("F", [1, 7, 40, 100])
+def test_big_oracle_csr_route_is_bit_identical_to_the_coo_loop(F):
+    """The claim oracle_big.py rests on: a row-wise loop over the stable CSR performs, for every
+    output element, the same fp32 operations in the same order as TF-CPU's sequential COO loop."""
+    import oracle_big
+    L = oracle_big.lib()
+    n, K, a = 500, 10, 0.1
+    edges, w = _random_graph(n, 6000, 1, hub=True)
+    big = oracle_big.BigOracle(edges, w, n, keep_idx=True)
+    H0 = np.random.default_rng(2).standard_normal((n, F)).astype(np.float32)
+    # normalisation and one SpMM, COO route
+    nv = oracle.get_adjacency(big.idx, big.raw, n)[1]
+    assert np.array_equal(big.norm_coo, nv)
+    P = np.zeros((n, F), np.float32)
+    L.oracle_spmm_coo_f32(big.idx.ctypes.data, big.norm_coo.ctypes.data, 0, big.nnz, H0.ctypes.data, F, P.ctypes.data)
+    assert np.array_equal(big.spmm(H0), P)
+    # K = 10 propagation, COO route (the C restatement of filter.py:17-22 under layered.py:52-55)
+    scratch = np.empty(big.nnz + n + n * F, np.float32)
+    out = np.empty((n, F), np.float32)
+    L.oracle_appnp_propagate_f32(big.idx.ctypes.data, big.raw.ctypes.data, big.nnz, n, H0.ctypes.data, F,
+                                 ctypes.c_float(a), K, 0, scratch.ctypes.data, out.ctypes.data)
+    assert np.array_equal(big.propagate(H0, a, K), out)
+    # and against the NumPy oracle within the fp32 tolerance
+    oracle.assert_close(out, oracle.appnp_propagate(big.idx, big.raw, n, H0, a, K)[-1], what="C vs NumPy K=10")
+    assert np.array_equal(big.step(H0, H0, a), big.propagate(H0, a, 1))
