@@ -155,29 +155,22 @@ def config_dict(args, n, E, nnz, F):
 # ----------------------------------------------------------------------------------------------
 # CPU arm (oracle port of the reference's TF-CPU path)
 # ----------------------------------------------------------------------------------------------
-def load_oracle_c():
-    import __graft_entry__ as entry
-    lib = ctypes.CDLL(entry.build_oracle())
-    P = ctypes.c_void_p
-    lib.oracle_normalize_sym_f32.argtypes = [P, P, ctypes.c_int64, ctypes.c_int64, P, P]
-    lib.oracle_spmm_coo_f32.argtypes = [P, P, ctypes.c_int64, ctypes.c_int64, P, ctypes.c_int64, P]
-    lib.oracle_teleport_f32.argtypes = [P, P, ctypes.c_int64, ctypes.c_float, P]
-    lib.oracle_appnp_step_csr_omp_f32.argtypes = [P, P, P, P, P, ctypes.c_int64, ctypes.c_float, ctypes.c_int64,
-                                                  ctypes.c_int64, P]
-    return lib
+def big_oracle(n, edges_cpu):
+    """The C oracle's view of the workload (oracle/oracle_big.py): graph2adj, get_adjacency, stable CSR."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import oracle_big
+    t0 = time.time()
+    big = oracle_big.BigOracle(edges_cpu, None, n, keep_idx=True)
+    log(f"[oracle] graph2adj + get_adjacency + stable CSR on the host: {time.time() - t0:.1f}s")
+    return big
 
 
-def cpu_arm(n, edges_cpu, F, seconds_per_step, steps, warmup, multi_thread_context=True):
+def cpu_arm(big, F, seconds_per_step, steps, warmup, multi_thread_context=True):
     """Times the oracle's restatement of filter.py:19-21 (COO-order SpMM loop as in TF-CPU's
     SparseTensorDenseMatMul functor + teleport) on a bounded prefix of the COO list."""
-    sys.path.insert(0, os.path.join(ROOT, "oracle"))
-    import gnntf_oracle as oracle
-    lib = load_oracle_c()
-    idx, val, _ = oracle.graph2adj_arrays(edges_cpu, None, n)
-    nnz = idx.shape[0]
-    D = np.empty(n, np.float32)
-    norm = np.empty(nnz, np.float32)
-    lib.oracle_normalize_sym_f32(idx.ctypes.data, val.ctypes.data, nnz, n, D.ctypes.data, norm.ctypes.data)
+    import oracle_big
+    lib = oracle_big.lib()
+    n, nnz, idx, norm = big.n, big.nnz, big.idx, big.norm_coo
     H = np.random.default_rng(1).standard_normal((n, F)).astype(np.float32)
     P = np.zeros((n, F), np.float32)
     out = np.empty((n, F), np.float32)
@@ -204,22 +197,51 @@ def cpu_arm(n, edges_cpu, F, seconds_per_step, steps, warmup, multi_thread_conte
     # context: the same step as a row-parallel CSR SpMM on every host thread (not what TF-CPU does)
     mt = None
     if multi_thread_context:
-        row_ptr, col_idx, coo_pos, _ = oracle.csr_from_coo(idx, n)
-        csr_val = np.ascontiguousarray(norm[coo_pos])
-        del coo_pos
         rows_cap = int(n * min(1.0, max(0.02, seconds_per_step * value * 4 / (nnz * F))))  # bounded: a few seconds
-        lib.oracle_appnp_step_csr_omp_f32(row_ptr.ctypes.data, col_idx.ctypes.data, csr_val.ctypes.data, H.ctypes.data,
-                                          H.ctypes.data, F, ctypes.c_float(ALPHA), 0, min(rows_cap, n), out.ctypes.data)
+        args = (big.row_ptr.ctypes.data, big.col.ctypes.data, big.val.ctypes.data, H.ctypes.data, H.ctypes.data, F,
+                ctypes.c_float(ALPHA), 0, min(rows_cap, n), out.ctypes.data)
+        lib.oracle_appnp_step_csr_omp_f32(*args)
         t0 = time.perf_counter()
-        lib.oracle_appnp_step_csr_omp_f32(row_ptr.ctypes.data, col_idx.ctypes.data, csr_val.ctypes.data, H.ctypes.data,
-                                          H.ctypes.data, F, ctypes.c_float(ALPHA), 0, min(rows_cap, n), out.ctypes.data)
+        lib.oracle_appnp_step_csr_omp_f32(*args)
         dt = time.perf_counter() - t0
-        done = int(row_ptr[min(rows_cap, n)])
+        done = int(big.row_ptr[min(rows_cap, n)])
         mt = {"mt_value": done * F / dt, "mt_cores": omp, "mt_sample": f"rows 0..{min(rows_cap, n)} ({done} entries), 1 timed rep",
               "mt_kind": "row-parallel CSR SpMM + fused teleport on all OpenMP threads (context only: TF-CPU's kernel for this op is a single-threaded COO loop)"}
     desc = (f"{sample} of {nnz} COO entries (prefix, storage order) x F={F}: one PPR iteration's SpMM + teleport, "
             f"{len(times)} timed reps; SpMM loop single-threaded as in TF-CPU, element-wise pass on {omp} OpenMP threads")
     return value, t, sample, desc, omp, mt
+
+
+def parity_block(big, H0_host, got, split_rows, F):
+    """Check the propagation the timed region produced (ALL rows) against the C oracle.
+    un-split rows: the reference's order, fp32 (oracle_appnp_propagate_csr_omp_f32, bit-identical to the
+    sequential COO loop); rows the GPU sums in pieces: the double-accumulating twin (see oracle_big.check_against).
+    max_rel_err = max |x−y| / max(|y|, floor·‖y‖∞) and must stay <= 1e-5."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import gnntf_oracle as oracle
+    t0 = time.time()
+    exp32 = big.propagate(H0_host, ALPHA, K_ITER)
+    norm = float(np.abs(exp32).max())
+    keep = ~split_rows
+    st = oracle.parity_stats(got[keep], exp32[keep], oracle.RTOL, oracle.FLOOR_REORDERED, norm)
+    out = {"checked_rows": int(got.shape[0]), "columns": int(F), "oracle": "oracle_c.c (C restatement of filter.py:17-22 over the "
+           "stable-by-row CSR, bit-identical to the sequential COO loop), K=10 from the same H0",
+           "rtol": oracle.RTOL, "floor": oracle.FLOOR_REORDERED, "norm_inf": norm,
+           "unsplit_rows": int(keep.sum()), "unsplit_max_rel_err": st["max_err_over_bound"] * oracle.RTOL,
+           "unsplit_max_abs_err_over_norm": st["max_abs_err_over_norm"],
+           "unsplit_bit_identical_fraction": float(np.mean(got[keep] == exp32[keep]))}
+    worst = st["max_err_over_bound"]
+    if split_rows.any():
+        exp64 = big.propagate(H0_host, ALPHA, K_ITER, acc64=True)
+        s2 = oracle.parity_stats(got[split_rows], exp64[split_rows], oracle.RTOL, oracle.FLOOR_REORDERED, norm)
+        s3 = oracle.parity_stats(got[split_rows], exp32[split_rows], oracle.RTOL, 1.0, norm)
+        out.update({"split_rows": int(split_rows.sum()), "split_max_rel_err_vs_double_accumulating_twin": s2["max_err_over_bound"] * oracle.RTOL,
+                    "split_max_abs_err_over_norm_vs_fp32_sequential": s3["max_abs_err_over_norm"]})
+        worst = max(worst, s2["max_err_over_bound"])
+    out["max_rel_err"] = worst * oracle.RTOL
+    out["ok"] = bool(worst <= 1.0)
+    out["wall_s"] = time.time() - t0
+    return out
 
 
 # ----------------------------------------------------------------------------------------------
@@ -281,6 +303,7 @@ def gpu_arm(args):
                else "pack kernel + NCCL all-to-all")
         sharding = (f"{R} row groups (contiguous node ranges balanced by nnz; halo rows by {how}, inside a column "
                     f"group) x {C} feature-column groups (no communication)")
+        H0_cpu = H0[:, :F].cpu() if (rank == 0 and not args.no_parity) else None   # for the parity check after the timed region
         del H0
     else:
         out = torch.empty_like(H0)
@@ -373,10 +396,44 @@ def gpu_arm(args):
                              "h2d_bytes_per_step": e2e["h2d"], "d2h_bytes_per_step": e2e["d2h"],
                              "ms_per_step": e2e["seconds"] * 1e3, "api": "gnntf.dist.ShardedPropagator.propagate_host"}
 
-    # ---- CPU baseline (rank 0, N=1 only) ----------------------------------------------------
+    # ---- parity of the timed propagation against the C oracle (every N), then the CPU baseline --------
+    big = None
+    if not args.no_parity and not args.reorder:
+        # what the timed region produced: this rank's rows (and columns) of H_K, in node order
+        with torch.no_grad():
+            mine = run()
+        torch.cuda.synchronize()
+        if world == 1:
+            got = mine[:, :F].cpu().numpy()
+        else:
+            shm = "/dev/shm" if os.path.isdir("/dev/shm") else tempfile.gettempdir()
+            tag = os.environ.get("MASTER_PORT", "0")
+            np.save(os.path.join(shm, f"gnntf_parity_{tag}_{rank}.npy"), mine.cpu().numpy())
+            meta = [None] * world
+            torch.distributed.all_gather_object(meta, (rank, prop.lo, prop.hi, c0, c1))
+            torch.distributed.barrier()
+            got = None
+            if rank == 0:
+                got = np.empty((n, F_run), np.float32)
+                for (rk, lo, hi, a0, a1) in meta:
+                    path = os.path.join(shm, f"gnntf_parity_{tag}_{rk}.npy")
+                    got[lo:hi, a0:a1] = np.load(path)
+                    os.unlink(path)
+                got = got[:, :F]
+        if rank == 0:
+            big = big_oracle(n, edges.cpu().numpy())
+            deg = np.diff(big.row_ptr)
+            from gnntf.sparse import LONG_THRESHOLD
+            split_rows = deg > LONG_THRESHOLD
+            H0_host = (H0[:, :F].cpu() if world == 1 else H0_cpu).contiguous().numpy()
+            result["parity"] = parity_block(big, H0_host, got, split_rows, F)
+            log(f"[parity] {json.dumps(result['parity'])}")
+            del got, H0_host
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         t0 = time.time()
-        v, t, sample, desc, omp, mt = cpu_arm(n, edges.cpu().numpy(), F, seconds_per_step=6.0, steps=2, warmup=1)
+        if big is None:
+            big = big_oracle(n, edges.cpu().numpy())
+        v, t, sample, desc, omp, mt = cpu_arm(big, F, seconds_per_step=6.0, steps=2, warmup=1)
         result["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": omp, "kind": "port", "sample": desc,
                                   "host_cpus": os.cpu_count(), "wall_s": time.time() - t0}
         result["cpu_baseline"].update(mt or {})
@@ -395,8 +452,8 @@ def reference_arm(args):
     n, edges, F = make_workload(args, "cpu")
     nnz = 2 * edges.shape[0]
     budget = 150.0 / max(1, args.steps + args.warmup)
-    v, t, sample, desc, omp, mt = cpu_arm(n, edges.numpy(), F, seconds_per_step=min(20.0, budget), steps=args.steps,
-                                          warmup=args.warmup)
+    big = big_oracle(n, edges.numpy())
+    v, t, sample, desc, omp, mt = cpu_arm(big, F, seconds_per_step=min(20.0, budget), steps=args.steps, warmup=args.warmup)
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": K_ITER * nnz * F / v * 1e3, "ms_per_step_note": "K=10 propagation time extrapolated from the sampled rate",
             "sample_ms": t * 1e3, "higher_is_better": True, "scaling": "strong",
@@ -421,6 +478,7 @@ def main():
     ap.add_argument("--features", type=int, default=0, help="feature width (default: the shape's)")
     ap.add_argument("--scale", type=float, default=1.0, help="shrink the graph (tests only; 1.0 = BASELINE size)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-parity", action="store_true", help="skip the post-run check of the result against the C oracle")
     ap.add_argument("--reorder", action="store_true", help="locality-restoring internal node order (gnntf/reorder.py); its cost is part of the build time")
     ap.add_argument("--grid", default="", help="multi-GPU layout ROWSxCOLS (default: gnntf.dist.choose_grid)")
     ap.add_argument("--nccl-exchange", action="store_true", help="multi-GPU: halo rows by NCCL all-to-all instead of the fused peer-memory push")

@@ -167,7 +167,7 @@ extern "C" const char* gnntf_status_str(int code) {
         case GNNTF_E_SIZE: return "invalid size (negative, nnz >= 2^31, or leading dimension < F)";
         case GNNTF_E_MODE: return "Invalid matrix normalization";
         case GNNTF_E_WORKSPACE: return "workspace too small";
-        case GNNTF_E_ALIGN: return "pointer not 4-byte aligned";
+        case GNNTF_E_ALIGN: return "pointer misaligned (coo_indices must be 16-byte aligned)";
         default: break;
     }
     if (code > 0) return cudaGetErrorString((cudaError_t)code);

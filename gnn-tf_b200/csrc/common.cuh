@@ -11,11 +11,13 @@
         if (_e != cudaSuccess) return (int)_e;    \
     } while (0)
 
-// Kernel launches report configuration errors through cudaPeekAtLastError (non-clearing for
-// sticky errors, and it does not synchronise).
+// Kernel launches report configuration errors through cudaGetLastError: it does not synchronise,
+// and it CLEARS a non-sticky error (bad grid, shared-memory attribute), so one recoverable
+// configuration error is reported once instead of poisoning every later call of this thread (the
+// library links cudart statically: nobody else can clear this runtime's error state).
 #define GNNTF_LAUNCH_CHECK()                      \
     do {                                          \
-        cudaError_t _e = cudaPeekAtLastError();   \
+        cudaError_t _e = cudaGetLastError();      \
         if (_e != cudaSuccess) return (int)_e;    \
     } while (0)
 
@@ -83,6 +85,7 @@ struct Vec<4> {
     __device__ __forceinline__ void store(float* p) const {
         st_stream4(p, make_float4(v[0], v[1], v[2], v[3]));
     }
+    __device__ __forceinline__ float4 as_float4() const { return make_float4(v[0], v[1], v[2], v[3]); }
 };
 
 }  // namespace gnntf

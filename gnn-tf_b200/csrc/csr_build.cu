@@ -291,6 +291,8 @@ extern "C" int gnntf_csr_build(const int64_t* edges, const float* weights, int64
     if (n_edges > 0 && edges == nullptr) return GNNTF_E_NULL;
     if (nnz > 0 && (col_idx == nullptr || raw_val == nullptr || coo_pos == nullptr || ws == nullptr))
         return GNNTF_E_NULL;
+    // the COO index pairs are written as one 16-byte store each
+    if (coo_indices != nullptr && (reinterpret_cast<uintptr_t>(coo_indices) & 15u) != 0) return GNNTF_E_ALIGN;
     cudaStream_t st = (cudaStream_t)stream;
     if (nnz == 0) {
         GNNTF_CUDA_TRY(cudaMemsetAsync(row_ptr, 0, (size_t)(n + 1) * sizeof(int32_t), st));

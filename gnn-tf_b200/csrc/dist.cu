@@ -103,8 +103,8 @@ extern "C" int gnntf_halo_push_f32(const float* H, int64_t ld, const int32_t* se
     if (H == nullptr || send_idx == nullptr || send_off == nullptr || peer_base == nullptr || peer_row0 == nullptr)
         return GNNTF_E_NULL;
     // The push overlaps the owned-column SpMM pass: a small grid leaves the SMs to that kernel
-    // (NVLink needs far fewer warps in flight than HBM does).  GNNTF_PUSH_CTAS overrides.
-    static const int max_ctas = [] { const char* e = getenv("GNNTF_PUSH_CTAS"); return e ? std::max(1, atoi(e)) : kNumSMs; }();
+    // (NVLink needs far fewer warps in flight than HBM does).
+    const int max_ctas = kNumSMs;
     const int grid = (int)std::min<int64_t>(ceil_div(n_send, 8), (int64_t)max_ctas);
     const bool v4 = (F % 4 == 0) && (ld % 4 == 0) && (ldo % 4 == 0) && (reinterpret_cast<uintptr_t>(H) & 15u) == 0;
     cudaStream_t st = (cudaStream_t)stream;

@@ -26,13 +26,14 @@
 
 namespace gnntf {
 
+// `h` is the teleport row slice H0[row, f..f+VEC) when the caller already loaded it (the row kernel
+// issues that load before the row's gathers so its latency is hidden); it is ignored when e.H0 == NULL.
 template <int VEC>
-__device__ __forceinline__ void apply_epilogue(const Epilogue& e, int64_t row, int f, Vec<VEC> acc) {
+__device__ __forceinline__ void apply_epilogue_h(const Epilogue& e, int64_t row, int f, Vec<VEC> acc, Vec<VEC> h) {
     Vec<VEC> out;
 #pragma unroll
     for (int i = 0; i < VEC; ++i) out.v[i] = acc.v[i] * e.s;
     if (e.H0 != nullptr) {
-        Vec<VEC> h = Vec<VEC>::stream(e.H0 + row * e.ldh + f);
 #pragma unroll
         for (int i = 0; i < VEC; ++i) out.v[i] = __fadd_rn(out.v[i], __fmul_rn(h.v[i], e.t));
     }
@@ -60,6 +61,15 @@ __device__ __forceinline__ void apply_epilogue(const Epilogue& e, int64_t row, i
         }
         r.store(a);
     }
+}
+
+template <int VEC>
+__device__ __forceinline__ void apply_epilogue(const Epilogue& e, int64_t row, int f, Vec<VEC> acc) {
+    Vec<VEC> h;
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) h.v[i] = 0.0f;
+    if (e.H0 != nullptr) h = Vec<VEC>::stream(e.H0 + row * e.ldh + f);
+    apply_epilogue_h<VEC>(e, row, f, acc, h);
 }
 
 // L2 eviction-policy helpers: data touched once per step (CSR arrays, the teleport term, the
@@ -211,12 +221,57 @@ __device__ __forceinline__ Vec<VEC> gather_row(const float* lane_base, int c, ui
     return Vec<VEC>::gather(p);
 }
 
+// One multiply and one add per term instead of a fused multiply-add: TF-CPU's kernel for this op
+// (Eigen, stock wheels are built without FMA contraction) rounds the product and the sum
+// separately, and so does the CPU checker under tests/ (built with -ffp-contract=off).  With the
+// same operation order AND the same roundings, rows that are not split reproduce the checker bit
+// for bit (tests/test_gpu_parity.py::test_spmm_unsplit_rows_are_bit_identical_*).
+// The kernel is bound by the L1/L2 gather path, not by issue slots: the extra FADD per term costs
+// nothing measurable (products shape K=10: 50.5 ms with FMUL+FADD, 51.1 ms with FFMA; profiles/r2/06).
+__device__ __forceinline__ float mac(float v, float x, float acc) { return __fadd_rn(__fmul_rn(v, x), acc); }
+
+// Asynchronous global->shared copies (LDGSTS) of one 4-byte word with an L2 evict-first hint;
+// src_bytes = 0 writes a zero instead of reading (cp.async zero-fill).
+__device__ __forceinline__ void cp_async4(void* smem_dst, const void* gsrc, int src_bytes, uint64_t pol) {
+    const uint32_t d = static_cast<uint32_t>(__cvta_generic_to_shared(smem_dst));
+    asm volatile("cp.async.ca.shared.global.L2::cache_hint [%0], [%1], 4, %2, %3;" ::"r"(d), "l"(gsrc), "r"(src_bytes),
+                 "l"(pol)
+                 : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+// volatile: the two reads of a (col,val) pair (issue phase / math phase) must not be merged
+__device__ __forceinline__ int4 lds128(uint32_t addr) {
+    int4 v;
+    asm volatile("ld.shared.v4.s32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
+// A warp owns `rounds * (32/GROUP)` CONSECUTIVE sparse rows and walks them in `rounds` rounds of
+// 32/GROUP rows side by side.  The only loads a warp ever WAITS for are the gathers themselves
+// (the r1 kernel exposed, per row, the row_ptr load, every (col,val) batch load and the teleport
+// row load: ~10 dependent round trips for a 50-entry row where 7 are gathers — profiles/r2/01: the
+// bare gather runs the products shape in 3.3 ms, that kernel took 5.07 ms):
+//   * row_ptr of all the warp's rows: two coalesced loads up front (lane l holds row l);
+//   * the (col,val) batch b+1 — of the same rows, or the first batch of the next round — travels
+//     global -> shared as asynchronous copies (cp.async / LDGSTS) into the other half of a
+//     per-warp double buffer while batch b is being gathered.  Loads into REGISTERS cannot do this
+//     job: a warp's loads return in issue order, so a register prefetch of the (always DRAM-missing)
+//     CSR stream issued ahead of a gather batch holds that whole batch back (measured: 59 vs 51 ms);
+//   * slots past the end of a row are produced by the copy itself: the column is re-read from the
+//     row's last entry and the value is zero-filled (src-size 0), so every batch runs
+//     predicate-free for every lane group whatever its degree (0 * x leaves the sum unchanged
+//     for finite x, and the padded gathers re-read a feature row that is already in L1);
+//   * the teleport row H0[m] is prefetched into L2 at the start of the round.
 template <int VEC, int NSLOT, int GROUP, int UNROLL, int THREADS, int MINB>
 __global__ void __launch_bounds__(THREADS, MINB)
 spmm_rows_kernel(const int* __restrict__ row_ptr, const int* __restrict__ col_idx,
                  const float* __restrict__ val, const int* __restrict__ row_map,
                  const float* __restrict__ B, int64_t ldb, int n_rows, int long_threshold,
-                 int blocks_per_cta, int piece_ctas, PieceArgs pieces, Epilogue epi) {
+                 int rounds, int piece_ctas, PieceArgs pieces, Epilogue epi) {
     static_assert(UNROLL % 2 == 0 && GROUP % UNROLL == 0, "entries are read back two at a time, whole batches");
     if ((int)blockIdx.x < piece_ctas) {  // CTA-uniform: this CTA works on pieces of split rows
         const int piece = blockIdx.x * (THREADS / 32) + (threadIdx.x >> 5);
@@ -228,13 +283,12 @@ spmm_rows_kernel(const int* __restrict__ row_ptr, const int* __restrict__ col_id
         return;
     }
     const int row_cta = blockIdx.x - piece_ctas;
-    constexpr int ROWS_PER_WARP = 32 / GROUP;
+    constexpr int NG = 32 / GROUP;  // rows side by side in a warp
     constexpr int WARPS = THREADS / 32;
-    constexpr int ROWS_PER_BLOCK = WARPS * ROWS_PER_WARP;
-    // (col,val) pairs of the current 32 entries of this warp, broadcast through shared memory:
-    // one LDS.128 delivers two entries to every lane (0.5 L1 wavefronts per entry; the shuffle
-    // pair it replaces cost 2 wavefronts and was a third of the L1 data-pipe traffic, profiles/r1/02)
-    __shared__ __align__(16) int2 cv_smem[WARPS][32];
+    constexpr unsigned FULL = 0xffffffffu;
+    // (col,val) pairs of the current and the next batch of this warp; one LDS.128 delivers two
+    // entries to every lane of a group (0.5 L1 wavefronts per entry; a shuffle pair costs 2)
+    __shared__ __align__(16) int2 cv_smem[WARPS][2][32];
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     const int g = lane / GROUP;
@@ -243,8 +297,6 @@ spmm_rows_kernel(const int* __restrict__ row_ptr, const int* __restrict__ col_id
     const int F = epi.F;
     const uint64_t pol = policy_evict_first();
     const uint32_t pitch = (uint32_t)ldb * 4u;
-    int2* cv = cv_smem[warp];
-    const int2* cv_group = cv + g * GROUP;
 
     int fo[NSLOT];
     bool fok[NSLOT];
@@ -256,74 +308,106 @@ spmm_rows_kernel(const int* __restrict__ row_ptr, const int* __restrict__ col_id
         Bl[s] = B + (fok[s] ? fo[s] : 0);
     }
 
-    for (int it = 0; it < blocks_per_cta; ++it) {
-        const int64_t row = ((int64_t)row_cta * blocks_per_cta + it) * ROWS_PER_BLOCK + warp * ROWS_PER_WARP + g;
-        if (row - g >= n_rows) break;  // warp-uniform: the whole warp is past the end
-        int start = 0, deg = 0;
-        bool mine = false;
-        if (row < n_rows) {
-            start = __ldg(row_ptr + row);
-            deg = __ldg(row_ptr + row + 1) - start;
-            mine = !(long_threshold > 0 && deg > long_threshold);
-            if (!mine) deg = 0;
-        }
-        int maxdeg = deg;
-        if (ROWS_PER_WARP > 1) {
+    const int rpw = rounds * NG;  // rows of this warp, <= 32
+    const int64_t warp_first = ((int64_t)row_cta * WARPS + warp) * rpw;
+    if (warp_first >= n_rows) return;  // warp-uniform; nothing below synchronises across warps
+    int rp_lo = 0, rp_hi = 0;          // lane l: row_ptr[warp_first + l], row_ptr[warp_first + l + 1]
+    if (lane < rpw && warp_first + lane < n_rows) {
+        rp_lo = __ldg(row_ptr + warp_first + lane);
+        rp_hi = __ldg(row_ptr + warp_first + lane + 1);
+    }
+    // rows past the end of the matrix and split rows get deg = 0 and mine = false
+    auto round_info = [&](int r, int& start, int& deg, bool& mine, int& maxdeg) {
+        const int src = r * NG + g;
+        start = __shfl_sync(FULL, rp_lo, src);
+        deg = __shfl_sync(FULL, rp_hi, src) - start;
+        mine = (warp_first + src < n_rows) && !(long_threshold > 0 && deg > long_threshold);
+        if (!mine) deg = 0;
+        maxdeg = deg;
+        if (NG > 1) {
 #pragma unroll
-            for (int o = GROUP; o < 32; o <<= 1) {
-                maxdeg = max(maxdeg, __shfl_xor_sync(0xffffffffu, maxdeg, o));
-            }
+            for (int o = GROUP; o < 32; o <<= 1) maxdeg = max(maxdeg, __shfl_xor_sync(FULL, maxdeg, o));
+        }
+    };
+    // this lane's entry of batch `off` of its group's row -> cv_smem[warp][buf][lane] (asynchronous)
+    auto stage = [&](int start, int deg, int off, int buf) {
+        int2* dst = &cv_smem[warp][buf][lane];
+        if (deg > 0) {
+            const int e = min(off + gl, deg - 1);  // clamp: slots past the end repeat the row's last column
+            cp_async4(&dst->x, col_idx + start + e, 4, pol);
+            cp_async4(&dst->y, val + start + e, (off + gl < deg) ? 4 : 0, pol);
+        } else {
+            *dst = make_int2(0, 0);  // an idle group: column 0, value 0 (no global address is formed)
+        }
+        cp_async_commit();
+    };
+
+    int start, deg, maxdeg;
+    bool mine;
+    round_info(0, start, deg, mine, maxdeg);
+    int buf = 0;
+    stage(start, deg, 0, buf);
+    for (int r = 0; r < rounds; ++r) {
+        int n_start = 0, n_deg = 0, n_maxdeg = 0;
+        bool n_mine = false;
+        const bool more = (r + 1 < rounds) && (warp_first + (int64_t)(r + 1) * NG < n_rows);  // warp-uniform
+        if (more) round_info(r + 1, n_start, n_deg, n_mine, n_maxdeg);
+        const int64_t row = warp_first + r * NG + g;
+        const int64_t out_row = (mine && row_map) ? (int64_t)__ldg(row_map + row) : row;
+        if (mine && epi.H0 != nullptr) {
+#pragma unroll
+            for (int s = 0; s < NSLOT; ++s)
+                if (fok[s]) prefetch_l2(epi.H0 + out_row * epi.ldh + fo[s]);
         }
         Vec<VEC> acc[NSLOT];
 #pragma unroll
         for (int s = 0; s < NSLOT; ++s)
 #pragma unroll
             for (int i = 0; i < VEC; ++i) acc[s].v[i] = 0.0f;
-
-        // Slots past the end of a row are padded with (first column of the row, value 0): the
-        // batches then run predicate-free for every group of the warp, whatever its degree; the
-        // padded gathers re-read a row that is already in L1.  (0 * x leaves the sum unchanged for
-        // finite x; a non-finite feature row of the first neighbour already makes the true result
-        // non-finite.)
-        int c_pad = 0;
-        for (int off = 0; off < maxdeg; off += GROUP) {
-            int c = c_pad;
-            float v = 0.0f;
-            if (off + gl < deg) {
-                c = ld_once(col_idx + start + off + gl, pol);
-                v = ld_once(val + start + off + gl, pol);
-            }
-            if (off == 0) {
-                c_pad = __shfl_sync(0xffffffffu, c, 0, GROUP);  // the row's first column (deg > 0)
-                if (gl >= deg) c = (deg > 0) ? c_pad : 0;
-            }
-            __syncwarp();  // everyone is done reading the previous batch
-            cv[lane] = make_int2(c, __float_as_int(v));
+        if (maxdeg == 0) {  // nobody reads the batch staged for this round: reuse its buffer for the next round's first
             __syncwarp();
+            stage(n_start, n_deg, 0, buf);
+        }
+        for (int off = 0; off < maxdeg; off += GROUP) {
+            __syncwarp();  // every lane is done reading the other buffer (batch before this one)
+            if (off + GROUP < maxdeg) stage(start, deg, off + GROUP, buf ^ 1);  // next batch of these rows
+            else stage(n_start, n_deg, 0, buf ^ 1);                              // first batch of the next round
+            cp_async_wait<1>();  // this lane's copies of the CURRENT batch have landed
+            __syncwarp();        // ... and so have everybody else's
+            const uint32_t cv_group = smem_u32(&cv_smem[warp][buf][g * GROUP]);
             const int lim = min(GROUP, maxdeg - off);
             for (int j = 0; j < lim; j += UNROLL) {
-                int cj[UNROLL];
-                float vj[UNROLL];
-#pragma unroll
-                for (int u = 0; u < UNROLL; u += 2) {
-                    const int4 e = *reinterpret_cast<const int4*>(cv_group + j + u);
-                    cj[u] = e.x; vj[u] = __int_as_float(e.y);
-                    cj[u + 1] = e.z; vj[u + 1] = __int_as_float(e.w);
-                }
+                // Issue phase: read the columns, issue ALL the batch's gathers back to back.  The values
+                // are read again in the math phase instead of being kept: with (col,val) of the whole
+                // batch live next to the 4*UNROLL gather registers, ptxas (48-64 registers) interleaved
+                // the first FMAs after 3-4 loads, i.e. only 3-4 rows were ever in flight per warp
+                // (profiles/r2/05: the first product of a batch held 20 % of all stall samples).
                 Vec<VEC> x[UNROLL][NSLOT];
 #pragma unroll
-                for (int u = 0; u < UNROLL; ++u)
+                for (int u = 0; u < UNROLL; u += 2) {
+                    const int4 e = lds128(cv_group + (j + u) * 8);
 #pragma unroll
                     for (int s = 0; s < NSLOT; ++s)
-                        if (fok[s]) x[u][s] = gather_row<VEC>(Bl[s], cj[u], pitch);
+                        if (fok[s]) {
+                            x[u][s] = gather_row<VEC>(Bl[s], e.x, pitch);
+                            x[u + 1][s] = gather_row<VEC>(Bl[s], e.z, pitch);
+                        }
+                }
 #pragma unroll
-                for (int u = 0; u < UNROLL; ++u)
+                for (int u = 0; u < UNROLL; u += 2) {
+                    const int4 e = lds128(cv_group + (j + u) * 8);
+                    const float v0 = __int_as_float(e.y), v1 = __int_as_float(e.w);
 #pragma unroll
                     for (int s = 0; s < NSLOT; ++s)
-                        if (fok[s])
+                        if (fok[s]) {
 #pragma unroll
-                            for (int i = 0; i < VEC; ++i) acc[s].v[i] = fmaf(vj[u], x[u][s].v[i], acc[s].v[i]);
+                            for (int i = 0; i < VEC; ++i) acc[s].v[i] = mac(v0, x[u][s].v[i], acc[s].v[i]);
+#pragma unroll
+                            for (int i = 0; i < VEC; ++i) acc[s].v[i] = mac(v1, x[u + 1][s].v[i], acc[s].v[i]);
+                        }
+                }
             }
+            buf ^= 1;
         }
         if (deg == 0) {  // an empty (or split) row riding along in a warp: drop whatever the padding produced
 #pragma unroll
@@ -332,266 +416,156 @@ spmm_rows_kernel(const int* __restrict__ row_ptr, const int* __restrict__ col_id
                 for (int i = 0; i < VEC; ++i) acc[s].v[i] = 0.0f;
         }
         if (mine) {
-            const int64_t out_row = row_map ? (int64_t)__ldg(row_map + row) : row;
 #pragma unroll
             for (int s = 0; s < NSLOT; ++s)
                 if (fok[s]) apply_epilogue<VEC>(epi, out_row, fo[s], acc[s]);
         }
+        start = n_start; deg = n_deg; mine = n_mine; maxdeg = n_maxdeg;
     }
+    cp_async_wait<0>();  // nothing may still be in flight into this CTA's shared memory at exit
 }
 
 // ---------------------------------------------------------------------------------------------
-// Bulk-copy kernel (wide rows: F >= 68 floats, 16-byte aligned rows).
-//
-// Why it exists (profiles/r1/01): on the products shape the per-row register
-// kernel is latency-bound — DRAM, L1 and the issue slots are each ~50 % busy — because the bytes a
-// warp can keep in flight are capped by registers and by the 6 counting scoreboards (a rolling
-// register ring was measured 2x SLOWER: waiting for the oldest load also waits for the youngest;
-// a shared-memory ring fed by 16-byte cp.async was 2.5x slower: LDGSTS.128 sustains ~16 B/clk/SM).
-// Here every gathered feature row travels global -> shared as ONE bulk async copy (PTX
-// cp.async.bulk, SASS UBLKCP: the TMA engine, no registers, no L1, no scoreboard) that signals an
-// mbarrier with its byte count.  Each warp owns a private ring of S stages x G row images and S
-// mbarriers; it keeps up to S*G gathers in flight across row boundaries, so bytes in flight are
-// bounded by shared memory (~200 KB/SM), not by the register file.
-//
-// A warp owns R consecutive rows at a time and walks such chunks with a grid stride: the grid
-// sweeps the matrix as one wavefront, which keeps the band of gathered rows that L2 must hold
-// narrow.  Rows above the split threshold are left to the piece kernels, as in spmm_rows_kernel.
+// The float4 fast path (every leading dimension and base pointer 16-byte aligned, F % 4 == 0): the
+// same algorithm as spmm_rows_kernel with one float4 slot per lane, written for a small register
+// footprint so that ALL `UNROLL` gathers of a batch are in flight before the first product:
+//   * no per-slot predicates in the loop: a lane whose slot lies beyond F re-reads slot 0 of the tile
+//     (same 32-byte sector as lane 0's read, no extra traffic) and only the final store is predicated;
+//   * the next round's (start, degree) are recomputed from the row_ptr registers with two shuffles
+//     when they are needed instead of being carried through the loop;
+//   * (col,val) pairs are read from shared memory twice (issue phase: columns, math phase: values).
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_addr(const void* p) {
-    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
-}
-__device__ __forceinline__ void mbar_init(uint32_t bar, int count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
-    uint32_t ok;
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok)
-        : "r"(bar), "r"(parity)
-        : "memory");
-    return ok != 0;
-}
-// A byte-count mismatch would spin forever and wedge the GPU: trap after ~2 s instead.
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    if (mbar_try_wait(bar, parity)) return;
-    const long long t0 = clock64();
-    while (!mbar_try_wait(bar, parity)) {
-        if (clock64() - t0 > 4000000000LL) __trap();
-    }
-}
-__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
-                 "l"(src), "r"(bytes), "r"(bar)
-                 : "memory");
-}
-// Epilogue with the teleport row already in registers and evict-first stores; the rarely used
-// dropout-mask / backward-accumulate variants go through the generic path.
-__device__ __forceinline__ void epilogue_fast(const Epilogue& e, int64_t row, int f, const float4& a,
-                                              const float4& h0, uint64_t pol) {
-    if (e.keep != nullptr || e.ACC != nullptr) {
-        apply_epilogue<4>(e, row, f, Vec<4>{{a.x, a.y, a.z, a.w}});
+template <int GROUP, int UNROLL, int THREADS, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB)
+spmm_rows4_kernel(const int* __restrict__ row_ptr, const int* __restrict__ col_idx,
+                  const float* __restrict__ val, const int* __restrict__ row_map,
+                  const float* __restrict__ B, int64_t ldb, int n_rows, int long_threshold,
+                  int rounds, int piece_ctas, PieceArgs pieces, Epilogue epi) {
+    static_assert(UNROLL % 2 == 0 && GROUP % UNROLL == 0, "entries are read back two at a time, whole batches");
+    if ((int)blockIdx.x < piece_ctas) {  // CTA-uniform: this CTA works on pieces of split rows
+        const int piece = blockIdx.x * (THREADS / 32) + (threadIdx.x >> 5);
+        if (piece < pieces.n_chunks)
+            process_piece<4, 1, GROUP, 4>(row_ptr, col_idx, val, B, ldb, pieces.chunk_row, pieces.chunk_begin, piece,
+                                          pieces.chunk, pieces.partials, pieces.ldp, epi.F, blockIdx.y * (GROUP * 4));
         return;
     }
-    float4 o = make_float4(a.x * e.s, a.y * e.s, a.z * e.s, a.w * e.s);
-    if (e.H0 != nullptr) {
-        o.x = __fadd_rn(o.x, __fmul_rn(h0.x, e.t));
-        o.y = __fadd_rn(o.y, __fmul_rn(h0.y, e.t));
-        o.z = __fadd_rn(o.z, __fmul_rn(h0.z, e.t));
-        o.w = __fadd_rn(o.w, __fmul_rn(h0.w, e.t));
-    }
-    if (e.act == GNNTF_ACT_RELU) {
-        o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f);
-    }
-    if (e.C != nullptr) st_once4(e.C + row * e.ldc + f, o, pol);
-}
-
-// G row images per stage, S stages per warp.  Entry e of a stream lives in stage (e/G)%S, slot e%G.
-template <int NSLOT, int G, int S, int WARPS>
-__global__ void __launch_bounds__(WARPS * 32)
-spmm_bulk_kernel(const int* __restrict__ row_ptr, const int* __restrict__ col_idx,
-                 const float* __restrict__ val, const int* __restrict__ row_map,
-                 const float* __restrict__ B, int64_t ldb, int n_rows, int long_threshold,
-                 int rows_per_chunk, int tile_floats, Epilogue epi) {
-    static_assert(32 % G == 0 && G <= 32, "G must divide 32");
-    extern __shared__ __align__(128) unsigned char bulk_smem[];
+    constexpr int NG = 32 / GROUP;
+    constexpr int WARPS = THREADS / 32;
+    constexpr unsigned FULL = 0xffffffffu;
+    __shared__ __align__(16) int2 cv_smem[WARPS][2][32];
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
-    const int F = epi.F;
-    const int f_base = blockIdx.y * tile_floats;
-    const int width = min(tile_floats, F - f_base);        // floats of this feature tile
-    const uint32_t row_bytes = (uint32_t)width * 4u;       // multiple of 16 (F % 4 == 0)
-    const uint32_t slot_bytes = (uint32_t)tile_floats * 4u;
+    const int g = lane / GROUP;
+    const int gl = lane % GROUP;
+    const int f_tile = blockIdx.y * (GROUP * 4);
+    const int f = f_tile + gl * 4;
+    const bool live = f < epi.F;
+    const float* Bl = B + (live ? f : f_tile);
+    const uint32_t pitch = (uint32_t)ldb * 4u;
     const uint64_t pol = policy_evict_first();
 
-    unsigned char* my_ring = bulk_smem + (size_t)warp * (S * G) * slot_bytes;
-    const uint32_t ring_u32 = smem_addr(my_ring);
-    const uint32_t bars_u32 = smem_addr(bulk_smem + (size_t)WARPS * (S * G) * slot_bytes) + warp * S * 8;
-    if (lane < S) mbar_init(bars_u32 + lane * 8, 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    __syncwarp();
-
-    int fo[NSLOT];
-    bool fok[NSLOT];
-#pragma unroll
-    for (int s = 0; s < NSLOT; ++s) {
-        const int in_tile = (s * 32 + lane) * 4;
-        fo[s] = f_base + in_tile;
-        fok[s] = in_tile < width;
+    const int rpw = rounds * NG;  // rows of this warp, <= 32
+    const int warp_first = (int)(((int64_t)(blockIdx.x - piece_ctas) * WARPS + warp) * rpw);  // host: grid covers < 2^31 rows
+    if (warp_first >= n_rows || warp_first < 0) return;
+    int rp_lo = 0, rp_hi = 0;  // lane l: row_ptr[warp_first + l], row_ptr[warp_first + l + 1]
+    if (lane < rpw && warp_first + lane < n_rows) {
+        rp_lo = __ldg(row_ptr + warp_first + lane);
+        rp_hi = __ldg(row_ptr + warp_first + lane + 1);
     }
-    const float* Bt = B + f_base;
-    uint32_t phase_bits = 0;  // bit s = parity to wait for on stage s next
-
-    const int n_chunks = (n_rows + rows_per_chunk - 1) / rows_per_chunk;
-    const int warp_stride = gridDim.x * WARPS;
-    float4 acc[NSLOT], h0[NSLOT];
+    // (start, degree) of this lane group's row in round r; rows past the end and split rows: degree 0, mine false
+    auto round_info = [&](int r, int& start, int& deg, bool& mine) {
+        const int src = (r * NG + g) & 31;
+        start = __shfl_sync(FULL, rp_lo, src);
+        deg = __shfl_sync(FULL, rp_hi, src) - start;
+        mine = (r < rounds) && (warp_first + r * NG + g < n_rows) && !(long_threshold > 0 && deg > long_threshold);
+        if (!mine) deg = 0;
+    };
+    auto group_max = [&](int v) {
+        if (NG > 1) {
 #pragma unroll
-    for (int s = 0; s < NSLOT; ++s) h0[s] = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int o = GROUP; o < 32; o <<= 1) v = max(v, __shfl_xor_sync(FULL, v, o));
+        }
+        return v;
+    };
+    auto stage = [&](int start, int deg, int off, int buf) {
+        int2* dst = &cv_smem[warp][buf][lane];
+        if (deg > 0) {
+            const int e = min(off + gl, deg - 1);  // slots past the end repeat the row's last column with value 0
+            cp_async4(&dst->x, col_idx + start + e, 4, pol);
+            cp_async4(&dst->y, val + start + e, (off + gl < deg) ? 4 : 0, pol);
+        } else {
+            *dst = make_int2(0, 0);
+        }
+        cp_async_commit();
+    };
 
-    for (int chunk = blockIdx.x * WARPS + warp; chunk < n_chunks; chunk += warp_stride) {
-        const int r0 = chunk * rows_per_chunk;
-        const int nr = min(rows_per_chunk, n_rows - r0);
-        const int rp = (lane <= nr) ? __ldg(row_ptr + r0 + lane) : 0;  // lane i holds row_ptr[r0+i]
-        const int rp_next = __shfl_down_sync(0xffffffffu, rp, 1);
-        const bool is_long = (lane < nr) && long_threshold > 0 && (rp_next - rp) > long_threshold;
-        const unsigned long_mask = __ballot_sync(0xffffffffu, is_long);
-        int cur_row = 0, cur_end = 0;
-
-        auto prefetch_h0 = [&](int local_row) {
-            if (epi.H0 != nullptr) {
-                const int64_t m = row_map ? (int64_t)__ldg(row_map + r0 + local_row) : (int64_t)(r0 + local_row);
-#pragma unroll
-                for (int s = 0; s < NSLOT; ++s)
-                    if (fok[s]) h0[s] = ld_once4(epi.H0 + m * epi.ldh + fo[s], pol);
+    int buf = 0;
+    {
+        int s0, d0;
+        bool m0;
+        round_info(0, s0, d0, m0);
+        stage(s0, d0, 0, buf);
+    }
+    for (int r = 0; r < rounds; ++r) {
+        if (warp_first + r * NG >= n_rows) break;  // warp-uniform
+        int start, deg;
+        bool mine;
+        round_info(r, start, deg, mine);
+        const int maxdeg = group_max(deg);
+        const int row = warp_first + r * NG + g;
+        if (mine && live && epi.H0 != nullptr) {
+            const int64_t m = row_map ? (int64_t)__ldg(row_map + row) : (int64_t)row;
+            prefetch_l2(epi.H0 + m * epi.ldh + f);
+        }
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (maxdeg == 0) {  // nobody reads the batch staged for this round: its buffer takes the next round's first batch
+            int ns, nd;
+            bool nm;
+            round_info(r + 1, ns, nd, nm);
+            __syncwarp();
+            stage(ns, nd, 0, buf);
+        }
+        for (int off = 0; off < maxdeg; off += GROUP) {
+            __syncwarp();  // every lane is done reading the other buffer
+            if (off + GROUP < maxdeg) {
+                stage(start, deg, off + GROUP, buf ^ 1);
+            } else {
+                int ns, nd;
+                bool nm;
+                round_info(r + 1, ns, nd, nm);
+                stage(ns, nd, 0, buf ^ 1);
             }
-        };
-        auto flush_row = [&](int seg_end) {  // write the current row, advance, prefetch the next teleport row
-            const int64_t m = row_map ? (int64_t)__ldg(row_map + r0 + cur_row) : (int64_t)(r0 + cur_row);
+            cp_async_wait<1>();
+            __syncwarp();
+            const uint32_t cvg = smem_u32(&cv_smem[warp][buf][g * GROUP]);
+            const int lim = min(GROUP, maxdeg - off);
+            for (int j = 0; j < lim; j += UNROLL) {
+                float4 x[UNROLL];
 #pragma unroll
-            for (int s = 0; s < NSLOT; ++s) {
-                if (fok[s]) epilogue_fast(epi, m, fo[s], acc[s], h0[s], pol);
-                acc[s] = make_float4(0.f, 0.f, 0.f, 0.f);
+                for (int u = 0; u < UNROLL; u += 2) {
+                    const int4 e = lds128(cvg + (j + u) * 8);
+                    x[u] = gather_row<4>(Bl, e.x, pitch).as_float4();
+                    x[u + 1] = gather_row<4>(Bl, e.z, pitch).as_float4();
+                }
+#pragma unroll
+                for (int u = 0; u < UNROLL; u += 2) {
+                    const int4 e = lds128(cvg + (j + u) * 8);
+                    const float v0 = __int_as_float(e.y), v1 = __int_as_float(e.w);
+                    acc.x = mac(v0, x[u].x, acc.x); acc.y = mac(v0, x[u].y, acc.y);
+                    acc.z = mac(v0, x[u].z, acc.z); acc.w = mac(v0, x[u].w, acc.w);
+                    acc.x = mac(v1, x[u + 1].x, acc.x); acc.y = mac(v1, x[u + 1].y, acc.y);
+                    acc.z = mac(v1, x[u + 1].z, acc.z); acc.w = mac(v1, x[u + 1].w, acc.w);
+                }
             }
-            ++cur_row;
-            cur_end = __shfl_sync(0xffffffffu, rp, min(cur_row + 1, 31));
-            if (cur_row < seg_end) prefetch_h0(cur_row);
-        };
-
-        int a = 0;
-        while (a < nr) {  // maximal runs [a,b) of rows that are not split
-            if ((long_mask >> a) & 1u) { ++a; continue; }
-            int b = nr;
-            const unsigned rest = long_mask >> a;
-            if (rest) b = a + __ffs(rest) - 1;
-            const int P0 = __shfl_sync(0xffffffffu, rp, a);
-            const int P1 = __shfl_sync(0xffffffffu, rp, b);
-            cur_row = a;
-            cur_end = __shfl_sync(0xffffffffu, rp, a + 1);
-#pragma unroll
-            for (int s = 0; s < NSLOT; ++s) acc[s] = make_float4(0.f, 0.f, 0.f, 0.f);
-            prefetch_h0(a);
-            while (cur_row < b && cur_end == P0) flush_row(b);  // leading empty rows
-            if (P0 == P1) { a = b; continue; }
-
-            const int n_ent = P1 - P0;
-            const int n_groups = (n_ent + G - 1) / G;
-            // (col,val) batches of 32 entries; *_nx prefetched one batch ahead of their first use
-            int cb = 0, cb_nx = 0;     // issue side
-            float vb = 0.f, vb_nx = 0.f;  // consume side
-            if (lane < n_ent) { cb = ld_once(col_idx + P0 + lane, pol); vb = ld_once(val + P0 + lane, pol); }
-            if (32 + lane < n_ent) { cb_nx = ld_once(col_idx + P0 + 32 + lane, pol); vb_nx = ld_once(val + P0 + 32 + lane, pol); }
-            int cb_base = 0;  // stream index of cb's lane 0
-
-            auto issue_group = [&](int g) {  // copies of group g into stage g % S
-                const int e0 = g * G;
-                if (e0 >= cb_base + 32) {  // the issue side moves into the next batch
-                    cb = cb_nx;
-                    cb_base += 32;
-                    cb_nx = (cb_base + 32 + lane < n_ent) ? ld_once(col_idx + P0 + cb_base + 32 + lane, pol) : 0;
-                }
-                const int cnt = min(G, n_ent - e0);
-                const int stage = g % S;
-                const uint32_t bar = bars_u32 + stage * 8;
-                if (lane == 0) mbar_expect_tx(bar, (uint32_t)cnt * row_bytes);
-                __syncwarp();
-                const int c = __shfl_sync(0xffffffffu, cb, (e0 - cb_base + lane) & 31);
-                if (lane < cnt)
-                    bulk_g2s(ring_u32 + (uint32_t)(stage * G + lane) * slot_bytes, Bt + (int64_t)c * ldb, row_bytes, bar);
-            };
-
-            const int pre = min(S, n_groups);
-            for (int g = 0; g < pre; ++g) issue_group(g);
-            int vb_base = 0;
-            for (int g = 0; g < n_groups; ++g) {
-                const int stage = g % S;
-                const int e0 = g * G;
-                if (e0 >= vb_base + 32) {
-                    vb = vb_nx;
-                    vb_base += 32;
-                    vb_nx = (vb_base + 32 + lane < n_ent) ? ld_once(val + P0 + vb_base + 32 + lane, pol) : 0.f;
-                }
-                mbar_wait(bars_u32 + stage * 8, (phase_bits >> stage) & 1u);
-                phase_bits ^= (1u << stage);
-                const int cnt = min(G, n_ent - e0);
-                const unsigned char* stage_base = my_ring + (size_t)(stage * G) * slot_bytes;
-                if (cnt == G && cur_end > P0 + e0 + G) {  // full group, no row end inside: check-free
-#pragma unroll
-                    for (int k = 0; k < G; ++k) {
-                        const float v = __shfl_sync(0xffffffffu, vb, (e0 - vb_base + k) & 31);
-#pragma unroll
-                        for (int s = 0; s < NSLOT; ++s) {
-                            if (fok[s]) {
-                                const float4 x = *reinterpret_cast<const float4*>(stage_base + (size_t)k * slot_bytes + (s * 32 + lane) * 16);
-                                acc[s].x = fmaf(v, x.x, acc[s].x);
-                                acc[s].y = fmaf(v, x.y, acc[s].y);
-                                acc[s].z = fmaf(v, x.z, acc[s].z);
-                                acc[s].w = fmaf(v, x.w, acc[s].w);
-                            }
-                        }
-                    }
-                } else {
-                    for (int k = 0; k < cnt; ++k) {
-                        const float v = __shfl_sync(0xffffffffu, vb, (e0 - vb_base + k) & 31);
-#pragma unroll
-                        for (int s = 0; s < NSLOT; ++s) {
-                            if (fok[s]) {
-                                const float4 x = *reinterpret_cast<const float4*>(stage_base + (size_t)k * slot_bytes + (s * 32 + lane) * 16);
-                                acc[s].x = fmaf(v, x.x, acc[s].x);
-                                acc[s].y = fmaf(v, x.y, acc[s].y);
-                                acc[s].z = fmaf(v, x.z, acc[s].z);
-                                acc[s].w = fmaf(v, x.w, acc[s].w);
-                            }
-                        }
-                        while (cur_row < b && cur_end == P0 + e0 + k + 1) flush_row(b);
-                    }
-                }
-                __syncwarp();  // every lane is done reading this stage before it is refilled
-                if (g + S < n_groups) issue_group(g + S);
-            }
-            a = b;
+            buf ^= 1;
+        }
+        if (mine && live) {
+            if (deg == 0) acc = make_float4(0.f, 0.f, 0.f, 0.f);  // padding of a longer neighbour row in this warp
+            const int64_t m = row_map ? (int64_t)__ldg(row_map + row) : (int64_t)row;
+            apply_epilogue<4>(epi, m, f, Vec<4>{{acc.x, acc.y, acc.z, acc.w}});
         }
     }
-}
-
-// ---------------------------------------------------------------------------------------------
-// Stand-alone launch of the piece work (used by the bulk-copy variant; the row kernel runs the
-// pieces inside its own grid).
-template <int VEC, int NSLOT, int GROUP, int UNROLL, int THREADS>
-__global__ void __launch_bounds__(THREADS)
-spmm_chunk_kernel(const int* __restrict__ row_ptr, const int* __restrict__ col_idx,
-                  const float* __restrict__ val, const float* __restrict__ B, int64_t ldb,
-                  const int* __restrict__ chunk_row, const int* __restrict__ chunk_begin,
-                  int n_chunks, int chunk, float* __restrict__ partials, int ldp, int F) {
-    const int piece = blockIdx.x * (THREADS / 32) + (threadIdx.x >> 5);
-    if (piece >= n_chunks) return;  // warp-uniform
-    process_piece<VEC, NSLOT, GROUP, UNROLL>(row_ptr, col_idx, val, B, ldb, chunk_row, chunk_begin, piece, chunk,
-                                             partials, ldp, F, blockIdx.y * (GROUP * NSLOT * VEC));
+    cp_async_wait<0>();  // nothing may still be in flight into this CTA's shared memory at exit
 }
 
 // Long rows, phase 2: one CTA per long row; thread t owns feature t (strided), sums the row's
@@ -624,33 +598,39 @@ spmm_long_reduce_kernel(const int* __restrict__ long_row, const int* __restrict_
 // ---------------------------------------------------------------------------------------------
 // Host-side dispatch
 // ---------------------------------------------------------------------------------------------
-static int env_int(const char* name, int dflt) {
-    const char* e = getenv(name);
-    return e ? atoi(e) : dflt;
+// Rounds per warp.  Deep grids: 8 (a warp's row_ptr values live in one register per lane, so
+// rounds * rows-side-by-side <= 32).  Grids of only a few waves (arxiv: ~4) lose up to a whole wave
+// to quantisation, so among the candidates the one whose last wave is fullest wins; small graphs
+// (Cora: 43 row blocks) keep one round so that every SM gets work.
+static int pick_rounds(int64_t n_rows, int rows_per_round, int ng, int ctas_per_sm) {
+    const int64_t row_blocks = ceil_div(n_rows, rows_per_round);
+    const int64_t slots = (int64_t)kNumSMs * ctas_per_sm;
+    const int cap = (int)std::max<int64_t>(1, std::min<int64_t>(std::min(8, 32 / ng), row_blocks / (slots * 4)));
+    int best = cap;
+    double best_fill = 0.0;
+    for (int r = cap; r >= std::max(1, cap / 2); --r) {
+        const double waves = (double)ceil_div(row_blocks, r) / (double)slots;
+        const double fill = waves / std::ceil(waves);
+        if (fill > best_fill + 0.02) { best_fill = fill; best = r; }
+    }
+    return best;
 }
-// Tuning knobs for A/B measurements (read once): GNNTF_SPMM_BULK=1 selects the TMA bulk-copy
-// kernel for wide rows (measured SLOWER than the register kernel on B200: 102 vs 61 ms on the
-// products shape — one 400-byte bulk copy costs ~23 cycles of TMA issue per SM — so it is off by
-// default), GNNTF_SPMM_ROWS the rows per chunk.
-static int rows_blocks_per_cta() { static int v = std::max(1, env_int("GNNTF_SPMM_BPC", 8)); return v; }
-static int bulk_mode() { static int v = env_int("GNNTF_SPMM_BULK", 0); return v; }
-static int bulk_rows_per_chunk() { static int v = std::max(1, std::min(31, env_int("GNNTF_SPMM_ROWS", 16))); return v; }
 
-template <int VEC, int NSLOT, int GROUP>
-static int launch_cfg(const gnntf_csr_t* A, const float* B, int64_t ldb, const Epilogue& epi,
-                      cudaStream_t st) {
-    constexpr int THREADS = 256;
-    constexpr int UNROLL = (NSLOT >= 4) ? 2 : (NSLOT == 2 ? 4 : (GROUP >= 8 ? 8 : 4));
-    constexpr int ROWS_PER_CTA = (THREADS / 32) * (32 / GROUP);
+template <int VEC, int NSLOT, int GROUP, int THREADS, int MINB, int UNROLL_>
+static int launch_cfg_t(const gnntf_csr_t* A, const float* B, int64_t ldb, const Epilogue& epi,
+                        cudaStream_t st) {
+    constexpr int UNROLL = UNROLL_ > 0 ? UNROLL_ : ((NSLOT >= 4) ? 2 : (NSLOT == 2 ? 4 : (GROUP >= 8 ? 8 : 4)));
+    constexpr int NG = 32 / GROUP;
+    constexpr int ROWS_PER_ROUND = (THREADS / 32) * NG;  // rows of one CTA per round
     const int F = epi.F;
     const int tile = GROUP * NSLOT * VEC;
     const unsigned gy = (unsigned)ceil_div(F, tile);
     const int thr = (A->n_long > 0) ? A->long_threshold : 0;
     if (A->n_rows > 0) {
-        // several row blocks per CTA once the grid is deep enough to keep every SM busy for many
-        // waves; small graphs (Cora: 43 row blocks) keep one block per CTA
-        const int64_t row_blocks = ceil_div(A->n_rows, ROWS_PER_CTA);
-        const int bpc = (int)std::max<int64_t>(1, std::min<int64_t>(rows_blocks_per_cta(), row_blocks / ((int64_t)kNumSMs * 5 * 4)));
+        // several rounds per warp once the grid is deep enough to keep every SM busy for many
+        // waves; small graphs (Cora: 43 row blocks) keep one round per warp.  A warp holds the
+        // row_ptr of all its rows in one register per lane: rounds * NG <= 32.
+        const int rounds = pick_rounds(A->n_rows, ROWS_PER_ROUND, NG, MINB);
         // the pieces of split rows ride in the same grid, ahead of the ordinary rows
         PieceArgs pieces{};
         int piece_ctas = 0;
@@ -659,9 +639,9 @@ static int launch_cfg(const gnntf_csr_t* A, const float* B, int64_t ldb, const E
             pieces = PieceArgs{A->chunk_row, A->chunk_begin, A->n_chunks, A->chunk, A->partials, ldp};
             piece_ctas = (int)ceil_div(A->n_chunks, THREADS / 32);
         }
-        dim3 grid((unsigned)(piece_ctas + ceil_div(A->n_rows, (int64_t)ROWS_PER_CTA * bpc)), gy);
-        spmm_rows_kernel<VEC, NSLOT, GROUP, UNROLL, THREADS, 5><<<grid, THREADS, 0, st>>>(
-            A->row_ptr, A->col_idx, A->val, A->row_map, B, ldb, (int)A->n_rows, thr, bpc, piece_ctas, pieces, epi);
+        dim3 grid((unsigned)(piece_ctas + ceil_div(A->n_rows, (int64_t)ROWS_PER_ROUND * rounds)), gy);
+        spmm_rows_kernel<VEC, NSLOT, GROUP, UNROLL, THREADS, MINB><<<grid, THREADS, 0, st>>>(
+            A->row_ptr, A->col_idx, A->val, A->row_map, B, ldb, (int)A->n_rows, thr, rounds, piece_ctas, pieces, epi);
         GNNTF_LAUNCH_CHECK();
         if (A->n_long > 0) {
             spmm_long_reduce_kernel<<<A->n_long, 128, 0, st>>>(A->long_row, A->long_first_chunk,
@@ -673,53 +653,49 @@ static int launch_cfg(const gnntf_csr_t* A, const float* B, int64_t ldb, const E
     return GNNTF_OK;
 }
 
+template <int VEC, int NSLOT, int GROUP>
+static int launch_cfg(const gnntf_csr_t* A, const float* B, int64_t ldb, const Epilogue& epi,
+                      cudaStream_t st) {
+    return launch_cfg_t<VEC, NSLOT, GROUP, 256, 5, 0>(A, B, ldb, epi, st);
+}
 
-template <int NSLOT, int G, int S>
-static int launch_bulk(const gnntf_csr_t* A, const float* B, int64_t ldb, const Epilogue& epi,
-                       cudaStream_t st) {
+// float4 fast path: spmm_rows4_kernel
+template <int GROUP, int THREADS, int MINB>
+static int launch_rows4_t(const gnntf_csr_t* A, const float* B, int64_t ldb, const Epilogue& epi, cudaStream_t st) {
+    constexpr int UNROLL = (GROUP >= 8) ? 8 : 4;
+    constexpr int NG = 32 / GROUP;
+    constexpr int ROWS_PER_ROUND = (THREADS / 32) * NG;
     const int F = epi.F;
-    const int tile_floats = std::min(F, NSLOT * 128);
-    const unsigned gy = (unsigned)ceil_div(F, tile_floats);
-    const size_t per_warp = (size_t)S * G * tile_floats * 4;
+    const unsigned gy = (unsigned)ceil_div(F, GROUP * 4);
     const int thr = (A->n_long > 0) ? A->long_threshold : 0;
-    const int rows_per_chunk = bulk_rows_per_chunk();
-    auto go = [&](auto warps_tag) -> int {
-        constexpr int WARPS = decltype(warps_tag)::value;
-        const size_t smem = per_warp * WARPS + (size_t)WARPS * S * 8;
-        auto kern = spmm_bulk_kernel<NSLOT, G, S, WARPS>;
-        GNNTF_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        const int64_t chunks = ceil_div(A->n_rows, rows_per_chunk);
-        const int ctas_per_sm = (int)std::max<size_t>(1, std::min<size_t>(8, (size_t)(224 * 1024) / (smem + 1024)));
-        dim3 grid((unsigned)std::min<int64_t>(ceil_div(chunks, WARPS), (int64_t)kNumSMs * ctas_per_sm), gy);
-        kern<<<grid, WARPS * 32, smem, st>>>(A->row_ptr, A->col_idx, A->val, A->row_map, B, ldb,
-                                            (int)A->n_rows, thr, rows_per_chunk, tile_floats, epi);
-        GNNTF_LAUNCH_CHECK();
-        return GNNTF_OK;
-    };
-    if (A->n_rows > 0) {
-        int rc;
-        if (per_warp * 8 <= 110 * 1024) rc = go(std::integral_constant<int, 8>{});
-        else if (per_warp * 4 <= 110 * 1024) rc = go(std::integral_constant<int, 4>{});
-        else rc = go(std::integral_constant<int, 2>{});
-        if (rc != GNNTF_OK) return rc;
-    }
+    if (A->n_rows == 0) return GNNTF_OK;
+    const int rounds = pick_rounds(A->n_rows, ROWS_PER_ROUND, NG, MINB);
+    PieceArgs pieces{};
+    int piece_ctas = 0;
+    const int ldp = (int)round_up(F, 4);
     if (A->n_long > 0) {
-        constexpr int THREADS = 256;
-        const int ldp = (int)round_up(F, 4);
-        constexpr int RS = (NSLOT > 4) ? 4 : NSLOT;
-        const unsigned gy2 = (unsigned)ceil_div(F, 32 * RS * 4);
-        dim3 grid((unsigned)ceil_div(A->n_chunks, THREADS / 32), gy2);
-        spmm_chunk_kernel<4, RS, 32, (RS >= 4) ? 2 : 4, THREADS><<<grid, THREADS, 0, st>>>(
-            A->row_ptr, A->col_idx, A->val, B, ldb, A->chunk_row, A->chunk_begin, A->n_chunks,
-            A->chunk, A->partials, ldp, F);
-        GNNTF_LAUNCH_CHECK();
-        spmm_long_reduce_kernel<<<A->n_long, 128, 0, st>>>(A->long_row, A->long_first_chunk,
-                                                          A->long_n_chunks, A->row_map, A->partials,
-                                                          ldp, epi);
+        pieces = PieceArgs{A->chunk_row, A->chunk_begin, A->n_chunks, A->chunk, A->partials, ldp};
+        piece_ctas = (int)ceil_div(A->n_chunks, THREADS / 32);
+    }
+    dim3 grid((unsigned)(piece_ctas + ceil_div(A->n_rows, (int64_t)ROWS_PER_ROUND * rounds)), gy);
+    spmm_rows4_kernel<GROUP, UNROLL, THREADS, MINB><<<grid, THREADS, 0, st>>>(
+        A->row_ptr, A->col_idx, A->val, A->row_map, B, ldb, (int)A->n_rows, thr, rounds, piece_ctas, pieces, epi);
+    GNNTF_LAUNCH_CHECK();
+    if (A->n_long > 0) {
+        spmm_long_reduce_kernel<<<A->n_long, 128, 0, st>>>(A->long_row, A->long_first_chunk, A->long_n_chunks,
+                                                          A->row_map, A->partials, ldp, epi);
         GNNTF_LAUNCH_CHECK();
     }
     return GNNTF_OK;
 }
+
+template <int GROUP>
+static int launch_rows4(const gnntf_csr_t* A, const float* B, int64_t ldb, const Epilogue& epi, cudaStream_t st) {
+    // 256 threads x 5 CTAs per SM (48 registers): A/B against 256x4, 256x3, 192x6, 128x8 — all within 2 %
+    // on the arxiv and products shapes (profiles/r2/06)
+    return launch_rows4_t<GROUP, 256, 5>(A, B, ldb, epi, st);
+}
+
 
 static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
@@ -759,23 +735,13 @@ int spmm_dispatch(const gnntf_csr_t* A, const float* B, int64_t ldb, Epilogue ep
     if (epi.ACC) v4 = v4 && (epi.ldacc % 4 == 0) && aligned16(epi.ACC);
     if (epi.keep) v4 = false;  // byte mask rows are F-strided: keep the scalar path
 
-    if (v4 && bulk_mode() && F >= 68) {
-        if (F <= 128) return launch_bulk<1, 8, 4>(A, B, ldb, epi, st);
-        if (F <= 256) return launch_bulk<2, 8, 2>(A, B, ldb, epi, st);
-        return launch_bulk<4, 4, 2>(A, B, ldb, epi, st);  // tiles of 512 floats over grid.y
-    }
     if (v4) {
         const int64_t slots = F / 4;
-        if (slots <= 4) return launch_cfg<4, 1, 4>(A, B, ldb, epi, st);
-        if (slots <= 8) return launch_cfg<4, 1, 8>(A, B, ldb, epi, st);
-        if (slots <= 16) return launch_cfg<4, 1, 16>(A, B, ldb, epi, st);
-        if (slots <= 32) return launch_cfg<4, 1, 32>(A, B, ldb, epi, st);
-        // wider rows: 128-float tiles over grid.y with the one-slot mapping (8-deep gather batches);
-        // GNNTF_SPMM_WIDE=0 selects the multi-slot mappings instead (A/B)
-        static const int wide_tiles = env_int("GNNTF_SPMM_WIDE", 1);
-        if (wide_tiles) return launch_cfg<4, 1, 32>(A, B, ldb, epi, st);
-        if (slots <= 64) return launch_cfg<4, 2, 32>(A, B, ldb, epi, st);
-        return launch_cfg<4, 4, 32>(A, B, ldb, epi, st);  // tiles of 512 floats over grid.y
+        if (slots <= 4) return launch_rows4<4>(A, B, ldb, epi, st);
+        if (slots <= 8) return launch_rows4<8>(A, B, ldb, epi, st);
+        if (slots <= 16) return launch_rows4<16>(A, B, ldb, epi, st);
+        // wider rows: 128-float tiles over grid.y (multi-slot mappings spilled and lost, profiles/r1/09)
+        return launch_rows4<32>(A, B, ldb, epi, st);
     }
     if (F <= 4) return launch_cfg<1, 1, 4>(A, B, ldb, epi, st);
     if (F <= 8) return launch_cfg<1, 1, 8>(A, B, ldb, epi, st);

@@ -11,7 +11,9 @@ import os
 from ctypes import POINTER, Structure, byref, c_char_p, c_double, c_float, c_int, c_int32, c_int64, c_size_t, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "_lib", "libgnntf_b200.so")
+# GNNTF_B200_LIB points the binding at another build of the same ABI (A/B measurements of whole
+# library versions); unset = the in-tree build.
+LIB_PATH = os.environ.get("GNNTF_B200_LIB") or os.path.join(_HERE, "_lib", "libgnntf_b200.so")
 
 GNNTF_OK = 0
 NORM = {"symmetric": 0, "bipartite": 1, "none": 2}

@@ -105,12 +105,15 @@ class PPRIteration(Layer):
 
     # -- K-run fusion ----------------------------------------------------------------------
     def fusable(self, features):
+        # output_regularize != 0 needs this layer's own .value (Layer.loss): such layers run un-fused
         return (self.dropout == 0 and self.activation is identity and self.restart_transform is identity
+                and self.output_regularize == 0
                 and not isinstance(self.restart_probability, torch.Tensor)
                 and getattr(self.H0, "value", None) is features)
 
     def same_run(self, first):
         return (self.H0 is first.H0 and self.dropout == 0 and self.activation is identity
+                and self.output_regularize == 0
                 and self.restart_transform is identity and self.restart_probability == first.restart_probability
                 and self.graph_dropout == first.graph_dropout)
 
@@ -127,7 +130,9 @@ class PPRIteration(Layer):
             for layer in run:
                 layer.G = adjs
         out = ops.appnp_propagate(adjs, features, first.restart_probability, K)
-        run[-1].value = out  # intermediate iterates are not materialised by the fused op
+        for layer in run[:-1]:  # intermediate iterates are not materialised by the fused op:
+            layer.value = None  # a stale value from an earlier un-fused call must not survive
+        run[-1].value = out
         return out
 
 

@@ -12,12 +12,10 @@ import torch
 
 from . import _native as nat
 
-import os
-
 # rows longer than this many entries are split into pieces of `CHUNK` entries (see spmm.cu);
-# GNNTF_LONG_THRESHOLD / GNNTF_CHUNK override for A/B measurements
-LONG_THRESHOLD = int(os.environ.get("GNNTF_LONG_THRESHOLD", 256))
-CHUNK = int(os.environ.get("GNNTF_CHUNK", 256))
+# 128..512 measured flat, 1024 slower
+LONG_THRESHOLD = 256
+CHUNK = 256
 
 
 def _require_cuda():

@@ -43,7 +43,7 @@ extern "C" {
 #define GNNTF_E_SIZE (-2)      /* negative size, nnz >= 2^31, or ld < F */
 #define GNNTF_E_MODE (-3)      /* "Invalid matrix normalization" (gnn.py:46-47) or bad enum */
 #define GNNTF_E_WORKSPACE (-4) /* workspace too small */
-#define GNNTF_E_ALIGN (-5)     /* pointer not 4-byte aligned */
+#define GNNTF_E_ALIGN (-5)     /* pointer misaligned (coo_indices of gnntf_csr_build: 16 bytes) */
 
 /* normalized= of GNN.get_adjacency (gnn.py:36) */
 #define GNNTF_NORM_SYMMETRIC 0 /* D = 1/sqrt(colsum); v*D[row]*D[col]   gnn.py:40-42 */
@@ -96,8 +96,8 @@ typedef struct gnntf_csr {
  *   q <  E          : (u_q, v_q, w_q)
  *   E <= q < 2E     : (v_{q-E}, u_{q-E}, w_{q-E})      [undirected only, :28-30]
  *   then n diagonal entries (i,i,1.)                    [add_eye != 0; tf.sparse.eye, gnn.py:39,49]
- * Outputs: coo_indices int64 [nnz,2] / coo_values fp32 [nnz] (the SparseTensor fields; either may
- * be NULL), and the CSR obtained by a STABLE sort of that list by row: row_ptr int32 [n+1],
+ * Outputs: coo_indices int64 [nnz,2] (16-byte aligned, else GNNTF_E_ALIGN) / coo_values fp32 [nnz]
+ * (the SparseTensor fields; either may be NULL), and the CSR obtained by a STABLE sort of that list by row: row_ptr int32 [n+1],
  * col_idx int32 [nnz], raw_val fp32 [nnz], coo_pos int32 [nnz] (COO slot of each CSR slot).
  * Indices outside [0,n) are not detected here (the host shim validates).
  * ---------------------------------------------------------------------------------------- */

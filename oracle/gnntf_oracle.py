@@ -299,10 +299,28 @@ def csr_from_coo(indices, n, directed=False):
 # --------------------------------------------------------------------------------------
 
 RTOL = 1e-5
-# Elements smaller than FLOOR·‖y‖∞ are held to the absolute bound RTOL·FLOOR·‖y‖∞ (SURVEY.md §8c:
-# |x−y| ≤ 1e-5·max(|y|, 1e-3·‖y‖∞)).  An element-wise relative error is unbounded where the
-# expected value crosses zero.
-FLOOR = 1e-3
+# Elements smaller than FLOOR·‖y‖∞ are held to the absolute bound RTOL·FLOOR·‖y‖∞.  SURVEY.md §8c
+# proposed FLOOR = 1e-3, i.e. an absolute bound of 1e-8·‖y‖∞ — below fp32's own resolution of the
+# norm (2^-24 = 6e-8): the fp32 oracle itself misses its fp64 twin by up to 3e-7·‖y‖∞ after K=10
+# steps (tests/test_oracle.py, measured), so no fp32 implementation (TF's included) can meet it.
+# Measured on the B200 (gpurun_out/parity_report_gpu.json, summarised in DESIGN.md §3): where both
+# sides accumulate in the same order the worst error is 1..3e-7·‖y‖∞ (a few ulps of the norm,
+# coming from the degree sums of randomly weighted test graphs), and EXACTLY ZERO for unit or
+# dyadic weights (the bit-identity tests).  Hence
+#   FLOOR = FLOOR_SAME_ORDER = 0.02   absolute bound 2e-7·‖y‖∞  (the tightest value that passes;
+#                                     0.01 fails 7 of 333 comparisons by at most 1.5x)
+#   FLOOR_REORDERED = 0.05            5e-7·‖y‖∞, stated at the call site wherever the summation order
+#                                     legitimately differs (fp64 twin, scipy, rows split into
+#                                     pieces, sharded two-pass accumulation).
+# Round 1 used 0.1 everywhere.
+FLOOR = 0.02
+FLOOR_SAME_ORDER = FLOOR
+FLOOR_REORDERED = 0.05 (5e-7·‖y‖∞) is
+# stated at the call site wherever the summation order legitimately differs (fp64 twin, scipy,
+# rows split into pieces, K-step chains that contain split rows).  Round 1 used 0.1 everywhere.
+FLOOR = 0.01
+FLOOR_SAME_ORDER = FLOOR
+FLOOR_REORDERED = 0.05
 
 # Every call appends {"what", "size", "max_abs_err_over_norm", "max_err_over_bound", "rtol",
 # "floor"}: tests/conftest.py writes the list to gpurun_out/parity_report.json at session end, so
@@ -310,12 +328,12 @@ FLOOR = 1e-3
 PARITY_LOG = []
 
 
-def parity_stats(actual, expected, rtol=RTOL, floor=FLOOR):
+def parity_stats(actual, expected, rtol=RTOL, floor=FLOOR, norm=None):
     a = np.asarray(actual, dtype=np.float64)
     e = np.asarray(expected, dtype=np.float64)
     if e.size == 0:
         return dict(size=0, norm=0.0, max_abs_err_over_norm=0.0, max_err_over_bound=0.0, worst=None)
-    norm = float(np.max(np.abs(e)))
+    norm = float(np.max(np.abs(e))) if norm is None else float(norm)
     bound = rtol * np.maximum(np.abs(e), floor * norm)
     err = np.abs(a - e)
     ratio = err / np.maximum(bound, 1e-300)
@@ -325,14 +343,14 @@ def parity_stats(actual, expected, rtol=RTOL, floor=FLOOR):
                 n_bad=int((err > bound).sum()))
 
 
-def assert_close(actual, expected, rtol=RTOL, what="", floor=FLOOR):
-    """|x−y| ≤ rtol·max(|y|, floor·‖y‖∞): the north_star's 1e-5 relative with SURVEY.md §8c's
-    norm-wise floor (default 1e-3·‖y‖∞) for elements near zero.  A test that needs a larger floor
-    says so at the call site, with the measured worst error."""
+def assert_close(actual, expected, rtol=RTOL, what="", floor=FLOOR, norm=None):
+    """|x−y| ≤ rtol·max(|y|, floor·‖y‖∞): the north_star's 1e-5 relative with a norm-wise floor for
+    elements near zero (see FLOOR above).  ``norm`` overrides ‖y‖∞ when ``expected`` is a slice of a
+    larger result (the floor then refers to the whole result's norm)."""
     a = np.asarray(actual)
     e = np.asarray(expected)
     assert a.shape == e.shape, f"{what}: shape {a.shape} vs {e.shape}"
-    st = parity_stats(a, e, rtol, floor)
+    st = parity_stats(a, e, rtol, floor, norm)
     PARITY_LOG.append(dict(what=what, size=st["size"], max_abs_err_over_norm=st["max_abs_err_over_norm"],
                            max_err_over_bound=st["max_err_over_bound"], rtol=rtol, floor=floor))
     if st["size"] and st["max_err_over_bound"] > 1.0:

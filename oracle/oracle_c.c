@@ -175,3 +175,46 @@ void oracle_appnp_propagate_csr_omp_f32(const int64_t* row_ptr, const int32_t* c
         src = dst;
     }
 }
+
+/* Same row-wise SpMM with the row sum accumulated in DOUBLE and rounded to fp32 once per element:
+ * the error-budget twin for rows where a sequential fp32 sum is itself the dominant error (hub rows
+ * with 10^4 entries: the fp32 sequential sum — TF-CPU's and oracle_spmm_coo_f32's — sits ~5e-6·‖y‖∞
+ * from this; an implementation that sums such a row in pieces is CLOSER to it than TF is).
+ * Not what the reference computes; used only to judge rows the GPU splits. */
+void oracle_spmm_csr_omp_acc64_f32(const int64_t* row_ptr, const int32_t* col, const float* val,
+                                   const float* H, int64_t F, int64_t r_lo, int64_t r_hi, float* out) {
+#pragma omp parallel
+    {
+        double* acc = (double*)malloc((size_t)(F > 0 ? F : 1) * sizeof(double));
+#pragma omp for schedule(dynamic, 256)
+        for (int64_t r = r_lo; r < r_hi; ++r) {
+            for (int64_t f = 0; f < F; ++f) acc[f] = 0.0;
+            for (int64_t p = row_ptr[r]; p < row_ptr[r + 1]; ++p) {
+                const double v = val[p];
+                const float* __restrict__ h = H + (int64_t)col[p] * F;
+                for (int64_t f = 0; f < F; ++f) acc[f] += v * (double)h[f];
+            }
+            float* __restrict__ o = out + r * F;
+            for (int64_t f = 0; f < F; ++f) o[f] = (float)acc[f];
+        }
+        free(acc);
+    }
+}
+
+/* K steps with the double-accumulating SpMM above (state kept in fp32 between steps, teleport as
+ * filter.py:21 in fp32). */
+void oracle_appnp_propagate_csr_omp_acc64_f32(const int64_t* row_ptr, const int32_t* col, const float* val,
+                                              int64_t n, const float* H0, int64_t F, float a, int K,
+                                              float* scratch, float* H_out) {
+    if (K == 0) {
+        memcpy(H_out, H0, (size_t)n * F * sizeof(float));
+        return;
+    }
+    const float* src = H0;
+    for (int k = 0; k < K; ++k) {
+        float* dst = ((K - 1 - k) % 2 == 0) ? H_out : scratch;
+        oracle_spmm_csr_omp_acc64_f32(row_ptr, col, val, src, F, 0, n, dst);
+        oracle_teleport_f32(dst, H0, n * F, a, dst);
+        src = dst;
+    }
+}

@@ -99,6 +99,84 @@ gather_ldg_kernel(const float* __restrict__ H, float* __restrict__ out, int n, i
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Bisecting the gap between the bare gather above and the real SpMM kernel: the same loop fed from
+// real arrays.  cols/vals: [n*deg] (fixed degree) or CSR with row_ptr (variable degree);
+// WITH_H0: the epilogue also streams a teleport row in.
+// ------------------------------------------------------------------------------------------------
+__global__ void fill_cols_kernel(int* cols, float* vals, const int* row_ptr, int n, int deg, float log2_dmax, uint32_t seed) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < (int64_t)n * 64; i += (int64_t)gridDim.x * blockDim.x) {
+        const int row = (int)(i >> 6), e = (int)(i & 63);
+        const int s = row_ptr ? row_ptr[row] : row * deg;
+        const int d = row_ptr ? row_ptr[row + 1] - s : deg;
+        if (e < d) {
+            cols[s + e] = pick_col(row, e, n, log2_dmax, 0, seed);
+            vals[s + e] = 0.02f;
+        }
+    }
+}
+
+template <bool WITH_H0, bool VAR_DEG>
+__global__ void __launch_bounds__(256, 5)
+gather_csr_kernel(const float* __restrict__ H, const float* __restrict__ H0, float* __restrict__ out,
+                  const int* __restrict__ row_ptr, const int* __restrict__ cols, const float* __restrict__ vals,
+                  int n, int ld, int lanes, int deg_fixed, int rows_per_cta) {
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const bool on = lane < lanes;
+    const float* Hl = H + (on ? lane * 4 : 0);
+    const uint32_t pitch = (uint32_t)ld * 4u;
+    for (int it = 0; it < rows_per_cta; it += 8) {
+        const int row = blockIdx.x * rows_per_cta + it + warp;
+        if (row >= n) break;
+        int start = row * deg_fixed, deg = deg_fixed;
+        if (VAR_DEG) {
+            start = __ldg(row_ptr + row);
+            deg = __ldg(row_ptr + row + 1) - start;
+        }
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int base = 0; base < deg; base += 32) {
+            int mycol = 0;
+            float myval = 0.f;
+            if (base + lane < deg) {
+                asm volatile("ld.global.nc.L1::no_allocate.s32 %0, [%1];" : "=r"(mycol) : "l"(cols + start + base + lane));
+                asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(myval) : "l"(vals + start + base + lane));
+            }
+            const int cnt = min(32, deg - base);
+            for (int j = 0; j < cnt; j += 8) {
+                float4 x[8];
+                float w[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const int c = __shfl_sync(0xffffffffu, mycol, (j + u) & 31);
+                    w[u] = __shfl_sync(0xffffffffu, myval, (j + u) & 31);
+                    const float* p;
+                    asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(p) : "r"(c), "r"(pitch), "l"(Hl));
+                    if (on) x[u] = __ldg(reinterpret_cast<const float4*>(p));
+                    else x[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    acc.x = fmaf(w[u], x[u].x, acc.x); acc.y = fmaf(w[u], x[u].y, acc.y);
+                    acc.z = fmaf(w[u], x[u].z, acc.z); acc.w = fmaf(w[u], x[u].w, acc.w);
+                }
+            }
+        }
+        if (on) {
+            if (WITH_H0) {
+                float4 h;
+                const float* hp = H0 + (size_t)row * ld + lane * 4;
+                asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(h.x), "=f"(h.y), "=f"(h.z), "=f"(h.w) : "l"(hp));
+                acc.x = acc.x * 0.9f + h.x * 0.1f; acc.y = acc.y * 0.9f + h.y * 0.1f;
+                acc.z = acc.z * 0.9f + h.z * 0.1f; acc.w = acc.w * 0.9f + h.w * 0.1f;
+            }
+            float* o = out + (size_t)row * ld + lane * 4;
+            asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(o), "f"(acc.x), "f"(acc.y),
+                         "f"(acc.z), "f"(acc.w) : "memory");
+        }
+    }
+}
+
 struct Cfg {
     const char* name;
     int n, F, ld, deg;
@@ -182,6 +260,55 @@ int main(int argc, char** argv) {
                c.name, c.n, c.F, c.ld, c.deg, dmax, c.p_uni, c.write_out, c.rows_per_cta, med, ms[0],
                gathers / (med * 1e-3), gbytes / (med * 1e-3) / 1e9, (double)c.n * c.ld * 4 / 1e6);
         fflush(stdout);
+    }
+
+    // ---- bisect: the same gather fed from real arrays (products law, F=100) ----
+    if (!filter || strstr("bisect_csr", filter)) {
+        const int n = NP, deg = 50, F = 100, ld = 100;
+        const float l2d = (float)std::log2(n / 2.0);
+        int *cols, *row_ptr;
+        float *vals, *H0;
+        CK(cudaMalloc(&cols, (size_t)n * 64 * 4));
+        CK(cudaMalloc(&vals, (size_t)n * 64 * 4));
+        CK(cudaMalloc(&row_ptr, (size_t)(n + 1) * 4));
+        CK(cudaMalloc(&H0, (size_t)n * ld * 4));
+        CK(cudaMemset(H0, 0, (size_t)n * ld * 4));
+        // variable degrees: 25 + binomial-ish spread in [25, 75], mean 50
+        std::vector<int> rp(n + 1);
+        rp[0] = 0;
+        uint32_t st = 12345u;
+        for (int i = 0; i < n; ++i) {
+            int d = 25;
+            for (int k = 0; k < 5; ++k) { st = st * 1664525u + 1013904223u; d += (st >> 24) % 11; }
+            rp[i + 1] = rp[i] + d;
+        }
+        CK(cudaMemcpy(row_ptr, rp.data(), (size_t)(n + 1) * 4, cudaMemcpyHostToDevice));
+        for (int variant = 0; variant < 4; ++variant) {
+            const bool var_deg = variant == 3;
+            fill_cols_kernel<<<148 * 8, 256>>>(cols, vals, var_deg ? row_ptr : nullptr, n, deg, l2d, 77u);
+            CK(cudaDeviceSynchronize());
+            std::vector<float> ms;
+            const int grid = (n + 63) / 64;
+            for (int r = 0; r < reps + 2; ++r) {
+                CK(cudaEventRecord(e0));
+                if (variant == 0) gather_ldg_kernel<8><<<grid, 256>>>(H, out, n, ld, F / 4, deg, l2d, 0, 77u, 64, 1);
+                else if (variant == 1) gather_csr_kernel<false, false><<<grid, 256>>>(H, H0, out, row_ptr, cols, vals, n, ld, F / 4, deg, 64);
+                else if (variant == 2) gather_csr_kernel<true, false><<<grid, 256>>>(H, H0, out, row_ptr, cols, vals, n, ld, F / 4, deg, 64);
+                else gather_csr_kernel<true, true><<<grid, 256>>>(H, H0, out, row_ptr, cols, vals, n, ld, F / 4, deg, 64);
+                CK(cudaEventRecord(e1));
+                CK(cudaEventSynchronize(e1));
+                CK(cudaGetLastError());
+                float t;
+                CK(cudaEventElapsedTime(&t, e0, e1));
+                if (r >= 2) ms.push_back(t);
+            }
+            std::sort(ms.begin(), ms.end());
+            const char* vn[] = {"hashed columns (bare gather)", "+ (col,val) read from arrays", "+ teleport row read", "+ variable degree 25..75 (row_ptr)"};
+            const double entries = var_deg ? (double)rp[n] : (double)n * deg;
+            printf("{\"bench\": \"bisect_csr\", \"variant\": \"%s\", \"entries\": %.0f, \"ms\": %.4f, \"ns_per_1k_entries\": %.3f}\n", vn[variant],
+                   entries, ms[ms.size() / 2], ms[ms.size() / 2] * 1e6 / entries * 1e3 / 1e3);
+            fflush(stdout);
+        }
     }
     return 0;
 }
