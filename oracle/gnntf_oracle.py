@@ -315,11 +315,6 @@ RTOL = 1e-5
 # Round 1 used 0.1 everywhere.
 FLOOR = 0.02
 FLOOR_SAME_ORDER = FLOOR
-FLOOR_REORDERED = 0.05 (5e-7·‖y‖∞) is
-# stated at the call site wherever the summation order legitimately differs (fp64 twin, scipy,
-# rows split into pieces, K-step chains that contain split rows).  Round 1 used 0.1 everywhere.
-FLOOR = 0.01
-FLOOR_SAME_ORDER = FLOOR
 FLOOR_REORDERED = 0.05
 
 # Every call appends {"what", "size", "max_abs_err_over_norm", "max_err_over_bound", "rtol",
