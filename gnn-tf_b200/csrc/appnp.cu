@@ -59,6 +59,13 @@ static int propagate_impl(const gnntf_csr_t* A_k, int n_adj, int K, const float*
         return GNNTF_OK;
     }
     if (K > 1 && scratch == nullptr && n > 0 && F > 0) return GNNTF_E_NULL;
+    if (n_adj == 1 && K > 1) {  // launch-bound shapes: all K steps in one cooperative launch
+        int rc = validate_csr(&A_k[0]);
+        if (rc != GNNTF_OK) return rc;
+        bool taken = false;
+        rc = spmm_persistent_propagate(&A_k[0], H0, H_out, scratch, ld, F, alpha, K, st, &taken);
+        if (rc != GNNTF_OK || taken) return rc;
+    }
     const float* src = H0;
     for (int k = 0; k < K; ++k) {
         float* dst = ((K - 1 - k) % 2 == 0) ? H_out : scratch;

@@ -22,6 +22,8 @@
 #include <cstdlib>
 #include <type_traits>
 
+#include <cooperative_groups.h>
+
 #include "spmm.cuh"
 
 namespace gnntf {
@@ -219,6 +221,16 @@ __device__ __forceinline__ Vec<VEC> gather_row(const float* lane_base, int c, ui
     const float* p;
     asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(p) : "r"(c), "r"(pitch_bytes), "l"(lane_base));
     return Vec<VEC>::gather(p);
+}
+
+template <bool COHERENT>
+__device__ __forceinline__ float4 gather_row4(const float* lane_base, int c, uint32_t pitch_bytes) {
+    const float* p;
+    asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(p) : "r"(c), "r"(pitch_bytes), "l"(lane_base));
+    if (!COHERENT) return __ldg(reinterpret_cast<const float4*>(p));
+    float4 v;
+    asm volatile("ld.global.cg.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+    return v;
 }
 
 // One multiply and one add per term instead of a fused multiply-add: TF-CPU's kernel for this op
@@ -435,29 +447,22 @@ spmm_rows_kernel(const int* __restrict__ row_ptr, const int* __restrict__ col_id
 //     when they are needed instead of being carried through the loop;
 //   * (col,val) pairs are read from shared memory twice (issue phase: columns, math phase: values).
 // ---------------------------------------------------------------------------------------------
-template <int GROUP, int UNROLL, int THREADS, int MINB>
-__global__ void __launch_bounds__(THREADS, MINB)
-spmm_rows4_kernel(const int* __restrict__ row_ptr, const int* __restrict__ col_idx,
-                  const float* __restrict__ val, const int* __restrict__ row_map,
-                  const float* __restrict__ B, int64_t ldb, int n_rows, int long_threshold,
-                  int rounds, int piece_ctas, PieceArgs pieces, Epilogue epi) {
+// COHERENT: the dense operand may have been written earlier in the SAME launch (the persistent
+// K-step kernel): its rows are then read with ld.global.cg (L2, always coherent) instead of the
+// read-only path.  `cta` = index of this CTA among the row CTAs, `f_tile` = first column of its tile.
+template <int GROUP, int UNROLL, int WARPS, bool COHERENT>
+__device__ __forceinline__ void rows4_body(const int* __restrict__ row_ptr, const int* __restrict__ col_idx,
+                                           const float* __restrict__ val, const int* __restrict__ row_map,
+                                           const float* __restrict__ B, int64_t ldb, int n_rows, int long_threshold,
+                                           int rounds, int64_t cta, int f_tile, const Epilogue& epi,
+                                           int2 (*cv_smem)[2][32]) {
     static_assert(UNROLL % 2 == 0 && GROUP % UNROLL == 0, "entries are read back two at a time, whole batches");
-    if ((int)blockIdx.x < piece_ctas) {  // CTA-uniform: this CTA works on pieces of split rows
-        const int piece = blockIdx.x * (THREADS / 32) + (threadIdx.x >> 5);
-        if (piece < pieces.n_chunks)
-            process_piece<4, 1, GROUP, 4>(row_ptr, col_idx, val, B, ldb, pieces.chunk_row, pieces.chunk_begin, piece,
-                                          pieces.chunk, pieces.partials, pieces.ldp, epi.F, blockIdx.y * (GROUP * 4));
-        return;
-    }
     constexpr int NG = 32 / GROUP;
-    constexpr int WARPS = THREADS / 32;
     constexpr unsigned FULL = 0xffffffffu;
-    __shared__ __align__(16) int2 cv_smem[WARPS][2][32];
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     const int g = lane / GROUP;
     const int gl = lane % GROUP;
-    const int f_tile = blockIdx.y * (GROUP * 4);
     const int f = f_tile + gl * 4;
     const bool live = f < epi.F;
     const float* Bl = B + (live ? f : f_tile);
@@ -465,7 +470,7 @@ spmm_rows4_kernel(const int* __restrict__ row_ptr, const int* __restrict__ col_i
     const uint64_t pol = policy_evict_first();
 
     const int rpw = rounds * NG;  // rows of this warp, <= 32
-    const int warp_first = (int)(((int64_t)(blockIdx.x - piece_ctas) * WARPS + warp) * rpw);  // host: grid covers < 2^31 rows
+    const int warp_first = (int)((cta * WARPS + warp) * rpw);  // host: the grid covers < 2^31 rows
     if (warp_first >= n_rows || warp_first < 0) return;
     int rp_lo = 0, rp_hi = 0;  // lane l: row_ptr[warp_first + l], row_ptr[warp_first + l + 1]
     if (lane < rpw && warp_first + lane < n_rows) {
@@ -544,8 +549,8 @@ spmm_rows4_kernel(const int* __restrict__ row_ptr, const int* __restrict__ col_i
 #pragma unroll
                 for (int u = 0; u < UNROLL; u += 2) {
                     const int4 e = lds128(cvg + (j + u) * 8);
-                    x[u] = gather_row<4>(Bl, e.x, pitch).as_float4();
-                    x[u + 1] = gather_row<4>(Bl, e.z, pitch).as_float4();
+                    x[u] = gather_row4<COHERENT>(Bl, e.x, pitch);
+                    x[u + 1] = gather_row4<COHERENT>(Bl, e.z, pitch);
                 }
 #pragma unroll
                 for (int u = 0; u < UNROLL; u += 2) {
@@ -566,6 +571,57 @@ spmm_rows4_kernel(const int* __restrict__ row_ptr, const int* __restrict__ col_i
         }
     }
     cp_async_wait<0>();  // nothing may still be in flight into this CTA's shared memory at exit
+}
+
+
+template <int GROUP, int UNROLL, int THREADS, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB)
+spmm_rows4_kernel(const int* __restrict__ row_ptr, const int* __restrict__ col_idx,
+                  const float* __restrict__ val, const int* __restrict__ row_map,
+                  const float* __restrict__ B, int64_t ldb, int n_rows, int long_threshold,
+                  int rounds, int piece_ctas, PieceArgs pieces, Epilogue epi) {
+    if ((int)blockIdx.x < piece_ctas) {  // CTA-uniform: this CTA works on pieces of split rows
+        const int piece = blockIdx.x * (THREADS / 32) + (threadIdx.x >> 5);
+        if (piece < pieces.n_chunks)
+            process_piece<4, 1, GROUP, 4>(row_ptr, col_idx, val, B, ldb, pieces.chunk_row, pieces.chunk_begin, piece,
+                                          pieces.chunk, pieces.partials, pieces.ldp, epi.F, blockIdx.y * (GROUP * 4));
+        return;
+    }
+    __shared__ __align__(16) int2 cv_smem[THREADS / 32][2][32];
+    rows4_body<GROUP, UNROLL, THREADS / 32, false>(row_ptr, col_idx, val, row_map, B, ldb, n_rows, long_threshold, rounds,
+                                                  (int64_t)blockIdx.x - piece_ctas, blockIdx.y * (GROUP * 4), epi, cv_smem);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Persistent K-step kernel for graphs whose whole step is ONE wave of CTAs (Cora, PubMed ...): the K
+// PPRIteration layers (filter.py:34-35 under layered.py:52-55) run inside one cooperative launch
+// with a grid-wide barrier between steps instead of K launches — those shapes are bound by launch
+// latency (r1: Cora 6.7 us per step for a 0.4 MB working set), not by memory.  Step k reads
+// buffer src_k and writes dst_k exactly as gnntf_appnp_propagate_f32 does (dst_{K-1} = H_out).
+// Buffers written inside the launch are gathered with ld.global.cg; no row is split (the host
+// takes this path only when the long-row plan is empty).
+// ---------------------------------------------------------------------------------------------
+template <int GROUP, int UNROLL, int THREADS, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB)
+appnp_persistent_kernel(const int* __restrict__ row_ptr, const int* __restrict__ col_idx,
+                        const float* __restrict__ val, const float* __restrict__ H0, float* __restrict__ H_out,
+                        float* __restrict__ scratch, int64_t ld, int n_rows, int rounds, int K, Epilogue epi) {
+    __shared__ __align__(16) int2 cv_smem[THREADS / 32][2][32];
+    cooperative_groups::grid_group grid = cooperative_groups::this_grid();
+    const float* src = H0;
+    for (int k = 0; k < K; ++k) {
+        float* dst = ((K - 1 - k) % 2 == 0) ? H_out : scratch;
+        Epilogue e = epi;
+        e.C = dst;
+        if (k == 0)
+            rows4_body<GROUP, UNROLL, THREADS / 32, false>(row_ptr, col_idx, val, nullptr, src, ld, n_rows, 0, rounds,
+                                                          (int64_t)blockIdx.x, blockIdx.y * (GROUP * 4), e, cv_smem);
+        else
+            rows4_body<GROUP, UNROLL, THREADS / 32, true>(row_ptr, col_idx, val, nullptr, src, ld, n_rows, 0, rounds,
+                                                         (int64_t)blockIdx.x, blockIdx.y * (GROUP * 4), e, cv_smem);
+        src = dst;
+        if (k + 1 < K) grid.sync();
+    }
 }
 
 // Long rows, phase 2: one CTA per long row; thread t owns feature t (strided), sums the row's
@@ -697,7 +753,64 @@ static int launch_rows4(const gnntf_csr_t* A, const float* B, int64_t ldb, const
 }
 
 
+
 static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+// Persistent K-step launch (appnp_persistent_kernel).  Returns GNNTF_OK and sets *taken when the
+// shape qualifies and the launch was enqueued; leaves *taken false otherwise (the caller then
+// issues K ordinary launches).
+template <int GROUP>
+static int try_persistent(const gnntf_csr_t* A, const float* H0, float* H_out, float* scratch, int64_t ld,
+                          const Epilogue& epi, int K, cudaStream_t st, bool* taken) {
+    constexpr int THREADS = 256, MINB = 5;
+    constexpr int UNROLL = (GROUP >= 8) ? 8 : 4;
+    constexpr int NG = 32 / GROUP;
+    auto kern = appnp_persistent_kernel<GROUP, UNROLL, THREADS, MINB>;
+    static int slots = -1;  // co-resident CTAs of this instantiation on the current device (0 = no cooperative launch)
+    if (slots < 0) {
+        int dev = 0, coop = 0, per_sm = 0, sms = 0;
+        GNNTF_CUDA_TRY(cudaGetDevice(&dev));
+        GNNTF_CUDA_TRY(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev));
+        GNNTF_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        GNNTF_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, THREADS, 0));
+        slots = coop ? per_sm * sms : 0;
+    }
+    const int64_t gy = ceil_div(epi.F, GROUP * 4);
+    int rounds = 1;
+    while (rounds < 32 / NG && ceil_div(A->n_rows, (int64_t)(THREADS / 32) * NG * rounds) * gy > slots) rounds *= 2;
+    const int64_t gx = ceil_div(A->n_rows, (int64_t)(THREADS / 32) * NG * rounds);
+    if (slots == 0 || gx * gy > slots) return GNNTF_OK;
+    const int* row_ptr = A->row_ptr;
+    const int* col_idx = A->col_idx;
+    const float* val = A->val;
+    int n_rows = (int)A->n_rows;
+    Epilogue e = epi;
+    void* args[] = {&row_ptr, &col_idx, &val, &H0, &H_out, &scratch, &ld, &n_rows, &rounds, &K, &e};
+    GNNTF_CUDA_TRY(cudaLaunchCooperativeKernel((void*)kern, dim3((unsigned)gx, (unsigned)gy), dim3(THREADS), args, 0, st));
+    *taken = true;
+    return GNNTF_OK;
+}
+
+int spmm_persistent_propagate(const gnntf_csr_t* A, const float* H0, float* H_out, float* scratch, int64_t ld,
+                              int64_t F, double alpha, int K, cudaStream_t st, bool* taken) {
+    *taken = false;
+    if (K < 2 || A->n_long > 0 || A->row_map != nullptr || A->n_rows <= 0 || F <= 0 || scratch == nullptr) return GNNTF_OK;
+    if (F % 4 != 0 || ld % 4 != 0 || ld >= (1LL << 30)) return GNNTF_OK;
+    if (!aligned16(H0) || !aligned16(H_out) || !aligned16(scratch)) return GNNTF_OK;
+    Epilogue e{};
+    e.s = (float)(1.0 - alpha);
+    e.H0 = H0;
+    e.ldh = ld;
+    e.t = (float)alpha;
+    e.act = GNNTF_ACT_IDENTITY;
+    e.ldc = ld;
+    e.F = (int)F;
+    const int64_t slots = F / 4;
+    if (slots <= 4) return try_persistent<4>(A, H0, H_out, scratch, ld, e, K, st, taken);
+    if (slots <= 8) return try_persistent<8>(A, H0, H_out, scratch, ld, e, K, st, taken);
+    if (slots <= 16) return try_persistent<16>(A, H0, H_out, scratch, ld, e, K, st, taken);
+    return try_persistent<32>(A, H0, H_out, scratch, ld, e, K, st, taken);
+}
 
 int validate_csr(const gnntf_csr_t* A) {
     if (A == nullptr) return GNNTF_E_NULL;

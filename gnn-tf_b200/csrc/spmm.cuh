@@ -25,5 +25,9 @@ struct Epilogue {
 
 int spmm_dispatch(const gnntf_csr_t* A, const float* B, int64_t ldb, Epilogue epi, cudaStream_t st);
 int validate_csr(const gnntf_csr_t* A);
+// K fused APPNP steps in ONE cooperative launch when the whole step is a single wave of CTAs and no
+// row is split; *taken says whether it was enqueued (otherwise the caller launches step by step).
+int spmm_persistent_propagate(const gnntf_csr_t* A, const float* H0, float* H_out, float* scratch, int64_t ld,
+                              int64_t F, double alpha, int K, cudaStream_t st, bool* taken);
 
 }  // namespace gnntf

@@ -619,6 +619,29 @@ def test_arrangement_recovers_hidden_locality():
     assert after < before / 20 and after < 3 * native, (before, after, native)
 
 
+@pytest.mark.parametrize("shape,F", [("cora", 7), ("cora", 64), ("pubmed", 3), ("pubmed", 64), ("pubmed", 100), ("pubmed", 500)])
+def test_persistent_k_step_kernel_equals_step_by_step(shape, F):
+    """Graphs whose step is a single wave of CTAs and that have no split rows run all K iterations in
+    ONE cooperative launch (appnp_persistent_kernel, grid barrier between steps).  The result must be
+    bit-identical to K separate fused-step launches and, through them, to the oracle."""
+    gnntf = _gnntf()
+    n, e, _, _ = synthetic.SHAPES[shape]
+    G = synthetic.citation_graph(n, e, seed=0)
+    adj = gnntf.graph2adj(G)
+    assert adj.csr.n_long == 0
+    A = adj.normalized("symmetric")
+    H0 = synthetic.features(n, F, seed=1, device="cuda")
+    for K in (2, 3, 10):
+        fused = gnntf.appnp_propagate(A, H0, 0.1, K)
+        H = H0
+        for _ in range(K):
+            H = gnntf.appnp_step(A, H, H0, 0.1)
+        assert torch.equal(fused, H), f"K={K}"
+    idx, val, _ = oracle.graph2adj(G)
+    expect = oracle.appnp_propagate(idx, val, n, _np(H0), 0.1, 10)[-1]
+    assert np.array_equal(_np(fused), expect), "no split rows, unit weights: bit-identical to the oracle"
+
+
 def test_propagation_is_bitwise_deterministic():
     """No float atomics on the undirected path: two runs (and a rebuilt adjacency) give identical bits,
     including rows split into pieces and the backward pass."""
