@@ -18,7 +18,7 @@ LIB_PATH = os.environ.get("GNNTF_B200_LIB") or os.path.join(_HERE, "_lib", "libg
 GNNTF_OK = 0
 NORM = {"symmetric": 0, "bipartite": 1, "none": 2}
 EYE = {"none": 0, "before": 1, "after": 2}
-ACT_IDENTITY, ACT_RELU = 0, 1
+ACT_IDENTITY, ACT_RELU, ACT_LEAKY_RELU = 0, 1, 2
 
 # every symbol include/gnntf_b200.h declares (checked by tests/test_abi.py)
 SYMBOLS = [
@@ -27,6 +27,7 @@ SYMBOLS = [
     "gnntf_appnp_step_f32", "gnntf_appnp_propagate_f32", "gnntf_appnp_propagate_multi_f32",
     "gnntf_appnp_propagate_bwd_f32", "gnntf_appnp_propagate_host_f32",
     "gnntf_halo_pack_f32", "gnntf_halo_push_f32", "gnntf_ipc_alloc", "gnntf_ipc_open", "gnntf_ipc_close", "gnntf_ipc_free",
+    "gnntf_bias_act_dropout_f32", "gnntf_bias_act_dropout_bwd_f32", "gnntf_node_xent_f32", "gnntf_node_xent_bwd_f32",
 ]
 
 
@@ -88,6 +89,13 @@ def lib():
     L.gnntf_halo_pack_f32.argtypes = [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_int64, c_void_p]
     L.gnntf_halo_push_f32.argtypes = [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int64, c_int64,
                                       c_int64, c_int64, c_void_p]
+    L.gnntf_bias_act_dropout_f32.argtypes = [c_void_p, c_int64, c_void_p, c_void_p, c_float, c_int, c_float, c_void_p,
+                                             c_int64, c_int64, c_int64, c_void_p]
+    L.gnntf_bias_act_dropout_bwd_f32.argtypes = [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_float, c_int, c_float,
+                                                 c_void_p, c_int64, c_int64, c_int64, c_void_p]
+    L.gnntf_node_xent_f32.argtypes = [c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_void_p]
+    L.gnntf_node_xent_bwd_f32.argtypes = [c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_void_p,
+                                          c_int64, c_void_p]
     L.gnntf_ipc_alloc.argtypes = [c_size_t, POINTER(c_void_p), c_void_p]
     L.gnntf_ipc_open.argtypes = [c_void_p, POINTER(c_void_p)]
     L.gnntf_ipc_close.argtypes = [c_void_p]

@@ -18,7 +18,8 @@ import torch
 import torch.nn.functional as tfn
 
 from . import ops
-from .nn import Dense, Dropout, Layer, Predictor, Trainable, as_tensor, identity, relu
+from .nn import (Concatenate, Dense, Dropout, Layer, Predictor, Trainable, as_tensor, dense_tail, identity, leaky_relu,
+                 relu)
 from .sparse import SparseAdjacency
 
 
@@ -96,9 +97,7 @@ class PPRIteration(Layer):
             propagated = ops.sparse_dense_matmul(self.G, features)         # filter.py:19
             out = propagated * (1 - a) + self.H0.value * a                 # filter.py:21
             return self.activation(architecture.dropout(out, self.dropout))
-        keep = None
-        if architecture.is_training() and self.dropout != 0:
-            keep = torch.rand(features.shape, device=features.device) >= float(self.dropout)
+        keep = architecture.dropout_mask(features.shape, self.dropout, features.device)
         fused_relu = self.activation in (relu, torch.relu, tfn.relu)
         out = ops.appnp_step(self.G, features, self.H0.value, a, keep, self.dropout, fused_relu)
         return out if (fused_relu or self.activation is identity) else self.activation(out)
@@ -166,13 +165,41 @@ class GCNLayer(Layer):
 
     def __forward__(self, gcn, features):
         adjacency = gcn.get_adjacency(self.graph_dropout)
-        if self.W.shape[1] < features.shape[1]:
-            # (Â·X)·W == Â·(X·W): when the layer narrows, propagate at the OUTPUT width (PubMed layer 1:
-            # SpMM at 64 columns instead of 500).  Same value up to fp32 rounding.
+        if _cacheable(gcn, adjacency, features):
+            transformed = aggregate_cached(gcn, adjacency, features) @ self.W                          # gcn.py:88, Â·X kept
+        elif self.W.shape[1] < features.shape[1]:
+            # (Â·X)·W == Â·(X·W): when the layer narrows, propagate at the OUTPUT width (PubMed layer 1 in
+            # training: SpMM at 64 columns instead of 500).  Same value up to fp32 rounding (SURVEY §8f-1;
+            # measured against the oracle's (ÂX)W in tests/test_gpu_fullsize.py).
             transformed = ops.sparse_dense_matmul(adjacency, features @ self.W)
         else:
-            transformed = ops.sparse_dense_matmul(adjacency, features) @ self.W                  # gcn.py:88
-        return gcn.dropout(self.activation(transformed + self.b), self.dropout)                  # gcn.py:89
+            transformed = ops.sparse_dense_matmul(adjacency, features) @ self.W                        # gcn.py:88
+        return dense_tail(gcn, transformed, self.b, self.activation, self.dropout)                     # gcn.py:89
+
+
+def _cacheable(gcn, adjacency, features):
+    return features is gcn.features and not adjacency.has_mask and not features.requires_grad
+
+
+def aggregate_cached(gcn, adjacency, features):
+    """``Â·X`` (gcn.py:88).  When X is the architecture's constant input matrix and Â carries no edge
+    mask (eval mode or graph_dropout = 0) the product is the same in every forward of every epoch: it
+    is computed once and kept on the adjacency (SURVEY §8f-1 "cache ÂX across epochs")."""
+    if _cacheable(gcn, adjacency, features):
+        cache = getattr(adjacency, "_agg_cache", None)
+        if cache is None or cache[0] is not features:
+            adjacency._agg_cache = (features, ops.sparse_dense_matmul(adjacency, features).detach())
+        return adjacency._agg_cache[1]
+    return ops.sparse_dense_matmul(adjacency, features)
+
+
+class GCNSpectralPreservingLayer(GCNLayer):
+    """gcn.py:93-105 — ``2·dropout(act((Â·X)·W + b) − b)``."""
+
+    def __forward__(self, gcn, features):
+        adjacency = gcn.get_adjacency(self.graph_dropout)
+        transformed = aggregate_cached(gcn, adjacency, features) @ self.W + self.b                       # gcn.py:104
+        return 2 * gcn.dropout(self.activation(transformed) - self.b, self.dropout)                     # gcn.py:105
 
 
 class GCN(GNN):
@@ -183,6 +210,136 @@ class GCN(GNN):
         for latent_dim in latent_dims:
             self.add(layer_type(latent_dim, graph_dropout=0.5, dropout=0.5))
         self.add(layer_type(num_classes))
+
+
+class Structural(Layer):
+    """gnn.py:5-26 — trainable per-node embeddings concatenated in front of the input features
+    (``GNN(preprocessor=Structural(...))``)."""
+
+    def __build__(self, architecture, dims: int = 16, l2_contraint: bool = False, bipartite: int = 0, **kwargs):
+        top_shape = architecture.top_shape()
+        self.l2_contraint = l2_contraint
+        self.embeddings = architecture.create_var((bipartite, dims), **kwargs)
+        self.embeddings2 = architecture.create_var((top_shape[0] - bipartite, dims), **kwargs)
+        return top_shape[0], dims + top_shape[1]
+
+    def __forward__(self, architecture, features):
+        embeddings = self.embeddings2
+        if self.embeddings.shape[0] != 0:
+            embeddings = torch.cat([self.embeddings, embeddings], dim=0)
+        if self.l2_contraint:
+            embeddings = l2_normalize(embeddings)
+        if features.shape[0] == 0:
+            return embeddings
+        return torch.cat([embeddings, features], dim=1)
+
+
+def l2_normalize(x, eps=1e-12):
+    """``tf.math.l2_normalize(x, axis=1)``: x · rsqrt(max(Σx², eps))."""
+    return x * torch.rsqrt(torch.clamp((x * x).sum(dim=1, keepdim=True), min=eps))
+
+
+def log1p(x):
+    """``tf.math.log1p`` on a Python float (the GCNII beta transformer default, gcn.py:9)."""
+    import math
+    return math.log1p(x)
+
+
+class GCNIILayer(Layer):
+    """gcn.py:7-27 — ``dropout(act(((1−a)·Â·X + a·H0) · ((1−b)·I + b·W)))``, b = beta_transformer(l/(k+1)).
+    The teleport mix is the fused PPR step kernel (same expression as filter.py:21)."""
+
+    def __build__(self, architecture, H0: Layer, a: float, l: float, k: int = 0, activation=identity,
+                  beta_transformer=log1p, dropout: float = 0.5, graph_dropout: float = 0.5, regularization=True):
+        dim = architecture.top_shape()[1]
+        self.W = architecture.create_var((dim, dim), "zero", regularize=regularization)
+        self.a, self.l, self.k = a, l, k
+        self.activation = activation
+        self.dropout = dropout
+        self.graph_dropout = graph_dropout
+        self.H0 = H0
+        self.beta_transformer = beta_transformer
+        return architecture.top_shape()
+
+    def _mix(self, gcn, features):
+        b = float(self.beta_transformer(self.l / (self.k + 1)))                                          # gcn.py:23
+        tradeoff = ops.appnp_step(gcn.get_adjacency(self.graph_dropout), features, self.H0.value, self.a)  # :24-25
+        eye = torch.eye(self.W.shape[1], dtype=self.W.dtype, device=self.W.device)
+        return tradeoff @ ((1 - b) * eye + b * self.W)                                                    # :26
+
+    def __forward__(self, gcn, features):
+        return dense_tail(gcn, self._mix(gcn, features), None, self.activation, self.dropout)             # gcn.py:27
+
+
+class GCNIISpectralPreservingLayer(GCNIILayer):
+    """gcn.py:30-51 — the same mix with a bias inside the activation and removed after it, doubled."""
+
+    def __build__(self, architecture, H0: Layer, a: float, l: float, k: int = 0, activation=identity,
+                  beta_transformer=log1p, dropout: float = 0.5, graph_dropout: float = 0.5, regularization=True):
+        shape = super().__build__(architecture, H0, a, l, k, activation, beta_transformer, dropout, graph_dropout,
+                                  regularization)
+        self.bias = architecture.create_var((1, architecture.top_shape()[1]), "zero")
+        return shape
+
+    def __forward__(self, gcn, features):
+        activation = self._mix(gcn, features) + self.bias                                                # gcn.py:50
+        return 2 * gcn.dropout(self.activation(activation) - self.bias, self.dropout)                     # gcn.py:51
+
+
+class GCNII(GNN):
+    """gcn.py:54-74 — Dropout → Dense(latent, relu)… → ``iterations`` × GCNIILayer(H0) → Dense(num_classes)."""
+
+    def __init__(self, graph, features, num_classes, a: float = 0.1, l: float = 0.5, latent_dims=[64], iterations=64,
+                 dropout=0.6, convolution_regularization=True, layer_type=GCNIILayer, **kwargs):
+        super().__init__(graph, features, **kwargs)
+        self.add(Dropout(dropout))
+        for latent_dim in latent_dims:
+            self.add(Dense(latent_dim, dropout=0, activation=relu))
+        H0 = self.top_layer()
+        for iteration in range(iterations):
+            self.add(layer_type(H0, a, l, iteration, activation=relu, dropout=dropout, graph_dropout=0,
+                                regularization=convolution_regularization))
+        self.add(Dense(num_classes, dropout=0, regularize=False))
+
+
+class NGCFLayer(Layer):
+    """gcn.py:116-135 — ``l2_normalize(dropout(act((X ∘ ÂX)·W1 + b1) + act((ÂX)·W2 + b2)))`` with the
+    bipartite-normalised adjacency drawn ONCE at build time (:127; with node_dropout ≠ 0 the mask drawn
+    then is kept for the layer's life, as in the reference)."""
+
+    def __build__(self, gcn, outputs: int, activation=leaky_relu, bias: bool = True, dropout: float = 0,
+                  node_dropout: float = 0, regularize: float = 1):
+        fan_in = gcn.top_shape()[0]
+        bound = 1. / fan_in ** 0.5
+        self.W1 = gcn.create_var((gcn.top_shape()[1], outputs), regularize=regularize, normalization=bound)
+        self.W2 = gcn.create_var((gcn.top_shape()[1], outputs), regularize=regularize, normalization=bound)
+        self.b1 = gcn.create_var((1, outputs), normalization=bound) if bias else 0
+        self.b2 = gcn.create_var((1, outputs), normalization=bound) if bias else 0
+        self.activation = activation
+        self.dropout = dropout
+        self.node_dropout = node_dropout
+        self.adjacency = gcn.get_adjacency(self.node_dropout, add_eye="none", normalized="bipartite")    # gcn.py:127
+        return (gcn.top_shape()[0], outputs)
+
+    def __forward__(self, gcn, features):
+        aggregated = ops.sparse_dense_matmul(self.adjacency, features)                                    # gcn.py:131
+        output = dense_tail(gcn, (features * aggregated) @ self.W1, self.b1, self.activation, 0) \
+            + dense_tail(gcn, aggregated @ self.W2, self.b2, self.activation, 0)                          # gcn.py:133-134
+        return l2_normalize(gcn.dropout(output, self.dropout))                                            # gcn.py:135
+
+
+class NGCF(GNN):
+    """gcn.py:138-153."""
+
+    def __init__(self, graph, features, num_classes: int, latent_dims=None, dropout=0.1, **kwargs):
+        super().__init__(graph, features, **kwargs)
+        if latent_dims is None:
+            latent_dims = [num_classes] * 2
+        layers = list()
+        for latent_dim in latent_dims:
+            layers.append(self.add(NGCFLayer(latent_dim, regularize=0.0, dropout=dropout, output_regularize=1)))
+        layers.append(self.add(NGCFLayer(num_classes, regularize=0.0, dropout=dropout, output_regularize=1)))
+        self.add(Concatenate(layers))
 
 
 class NodeClassification(Predictor):
@@ -208,6 +365,10 @@ class NodeClassification(Predictor):
             raise Exception("Evaluation requires node labels")
         if self.loss_transform is not None:
             features = self.loss_transform(features)
+        if features.is_cuda and features.dtype == torch.float32 and features.dim() == 2:
+            # embedding_lookup + log_softmax + sparse CE in one native kernel (csrc/dense.cu)
+            return ops.node_cross_entropy(features, as_tensor(self.nodes, dtype=torch.long, device=features.device),
+                                          self._labels(features.device))
         predictions = tfn.log_softmax(self._rows(features), dim=1)
         return tfn.cross_entropy(predictions, self._labels(features.device))  # from_logits CE on log-probs
 

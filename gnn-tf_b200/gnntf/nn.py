@@ -37,6 +37,11 @@ def relu(x):
     return torch.relu(x)
 
 
+def leaky_relu(x):
+    """``tf.nn.leaky_relu`` (alpha = 0.2), the NGCFLayer default (gcn.py:117)."""
+    return tfn.leaky_relu(x, 0.2)
+
+
 # ------------------------------------------------------------------------------------------
 # variables.py
 # ------------------------------------------------------------------------------------------
@@ -159,11 +164,20 @@ class Layered(VariableGenerator):
     def __exit__(self, exc_type, exc, tb):
         self.__training = False
 
+    def dropout_mask(self, shape, dropout, device=None):
+        """The keep-mask ``tf.nn.dropout`` would draw for a tensor of this shape (layered.py:44-45): None in
+        eval mode or for rate 0, else one independent Bernoulli(1-rate) per element.  Every dropout of the
+        stack goes through here (tests inject masks by overriding it)."""
+        if not self.__training or dropout == 0:
+            return None
+        return torch.rand(tuple(shape), device=device or default_device()) >= float(dropout)
+
     def dropout(self, features, dropout=0.5):
         """layered.py:44-45 — ``tf.nn.dropout`` only in training mode and for a non-zero rate."""
-        if not self.__training or dropout == 0:
+        keep = self.dropout_mask(features.shape, dropout, features.device)
+        if keep is None:
             return features
-        return tfn.dropout(features, p=float(dropout), training=True)
+        return features * keep.to(features.dtype) * (1.0 / (1.0 - float(dropout)))
 
     def sparse_dropout(self, G, dropout=0.5):
         """layered.py:47-50 — dropout on the nnz value vector, one draw per COO entry.  Returns the
@@ -233,7 +247,28 @@ class Dense(Layer):
         return (architecture.top_shape()[0], outputs)
 
     def __forward__(self, architecture, features):
-        return architecture.dropout(self.activation(features @ self.W + self.b), self.dropout)
+        return dense_tail(architecture, features @ self.W, self.b, self.activation, self.dropout)      # layers.py:136
+
+
+def dense_tail(architecture, Z, bias, activation, dropout):
+    """``dropout(activation(Z + b))`` (layers.py:136, gcn.py:89).  One native kernel for the activations
+    that have a code (identity / relu / leaky_relu) on CUDA fp32 inputs; any other callable runs eagerly."""
+    name = _activation_name(activation)
+    if name is None or not Z.is_cuda or Z.dtype != torch.float32:
+        return architecture.dropout(activation(Z + bias), dropout)
+    from . import ops
+    keep = architecture.dropout_mask(Z.shape, dropout, Z.device)
+    return ops.bias_act_dropout(Z, bias if isinstance(bias, torch.Tensor) else None, name, keep, dropout)
+
+
+def _activation_name(fn):
+    if fn is identity:
+        return "identity"
+    if fn in (relu, torch.relu, tfn.relu):
+        return "relu"
+    if fn is leaky_relu:  # (torch's own leaky_relu defaults to another slope: it runs eagerly)
+        return "leaky_relu"
+    return None
 
 
 class Dropout(Layer):
@@ -258,6 +293,29 @@ class Activation(Layer):
 
     def __forward__(self, gcn, features):
         return self.activation(features)
+
+
+class Concatenate(Layer):
+    """layers.py:86-101.  Quirk kept: ``__build__`` reports a column-wise concatenation (:93,96) while
+    ``__forward__`` concatenates along axis 0 (:100-101), exactly as the reference does."""
+
+    def __build__(self, architecture, H0):
+        self.H0 = H0
+        if isinstance(H0, list):
+            for H in H0:
+                if architecture.top_shape()[0] != H.output_shape[0]:
+                    raise Exception("Mismatching first dimension to concatenate between shapes " + str(architecture.top_shape())
+                                    + " and " + str(H.output_shape))
+            return (architecture.top_shape()[0], architecture.top_shape()[1] + H0[0].output_shape[1])
+        if architecture.top_shape()[0] != H0.output_shape[0]:
+            raise Exception("Mismatching first dimension to concatenate between shapes " + str(architecture.top_shape())
+                            + " and " + str(H0.output_shape))
+        return (architecture.top_shape()[0], architecture.top_shape()[1] + H0.output_shape[1])
+
+    def __forward__(self, architecture, features):
+        if isinstance(self.H0, list):
+            return torch.cat([H.value for H in self.H0], dim=0)
+        return torch.cat([features, self.H0.value], dim=0)
 
 
 # ------------------------------------------------------------------------------------------
@@ -330,12 +388,15 @@ class Trainable(Layered):
                             batch_loss = batch_loss + regularization * w.regularize * 0.5 * (w.var ** 2).sum()
                     (batch_loss * degradation(epoch)).backward()
                     optimizer.step()
-                    epoch_loss += float(batch_loss.detach())
+                    epoch_loss = epoch_loss + batch_loss.detach()   # stays on the device
             with torch.no_grad():
                 output = self(self.features)  # eval-mode forward (mode dropped by __exit__)
+                # the only host synchronisation of the epoch: the early-stopping decision needs the validation
+                # loss on the host (trainable.py:84,96-100); the reference also syncs for the training loss (:80)
                 valid_loss = float(valid.loss(output))
             patience_remaining -= 1
             if verbose and valid_loss < best_loss:
+                epoch_loss = float(epoch_loss)
                 train_acc = float(train.evaluate(output))
                 test_acc = float("nan") if test is None else float(test.evaluate(output))
                 valid_acc = float(valid.evaluate(output))

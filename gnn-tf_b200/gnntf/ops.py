@@ -235,3 +235,82 @@ def appnp_propagate_host(adj, H0_host, alpha=0.1, iterations=10, out_host=None, 
               "appnp_propagate_host")
     torch.cuda.current_stream().synchronize()
     return out_host
+
+
+# ------------------------------------------------------------------------------------------
+# Fused element-wise stages either side of the path (csrc/dense.cu)
+# ------------------------------------------------------------------------------------------
+_ACT_CODES = {"identity": nat.ACT_IDENTITY, "relu": nat.ACT_RELU, "leaky_relu": nat.ACT_LEAKY_RELU}
+
+
+class _BiasActDropout(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, Z, bias, keep, p_scale, act, slope):
+        L = nat.lib()
+        Z = _dense(Z)
+        n, F = Z.shape
+        out = torch.empty((n, F), dtype=torch.float32, device=Z.device)
+        b = None if bias is None else bias.reshape(-1).contiguous()
+        nat.check(L.gnntf_bias_act_dropout_f32(nat.ptr(Z), _ld(Z), nat.ptr(b), nat.ptr(keep), float(p_scale), int(act),
+                                               float(slope), nat.ptr(out), F, n, F, nat.stream_ptr()), "bias_act_dropout")
+        ctx.keep, ctx.p_scale, ctx.act, ctx.slope = keep, float(p_scale), int(act), float(slope)
+        ctx.has_bias, ctx.bias_shape = bias is not None, (None if bias is None else tuple(bias.shape))
+        ctx.save_for_backward(out if act != nat.ACT_IDENTITY else torch.empty(0, device=Z.device))
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        L = nat.lib()
+        (y,) = ctx.saved_tensors
+        g = _dense(g)
+        n, F = g.shape
+        dZ = torch.empty((n, F), dtype=torch.float32, device=g.device)
+        yy = y if y.numel() else None
+        nat.check(L.gnntf_bias_act_dropout_bwd_f32(nat.ptr(g), _ld(g), nat.ptr(yy), F, nat.ptr(ctx.keep), ctx.p_scale, ctx.act,
+                                                   ctx.slope, nat.ptr(dZ), F, n, F, nat.stream_ptr()), "bias_act_dropout_bwd")
+        db = dZ.sum(0).reshape(ctx.bias_shape) if (ctx.has_bias and ctx.needs_input_grad[1]) else None
+        return (dZ if ctx.needs_input_grad[0] else None), db, None, None, None, None
+
+
+def bias_act_dropout(Z, bias=None, activation="identity", keep=None, rate=0.0, slope=0.2):
+    """``dropout(activation(Z + bias))`` in one kernel (layers.py:135-136, gcn.py:89).  ``keep``: bool/uint8
+    [n,F] mask of the elements that survive (None = no dropout); ``rate`` gives the 1/(1-rate) scale."""
+    p_scale = 1.0
+    if keep is not None:
+        keep = keep.to(torch.uint8).contiguous()
+        p_scale = 1.0 / (1.0 - float(rate))
+    return _BiasActDropout.apply(Z, bias, keep, p_scale, _ACT_CODES[activation], slope)
+
+
+class _NodeXent(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, logits, nodes, labels):
+        L = nat.lib()
+        logits = _dense(logits)
+        m, C = int(nodes.numel()), logits.shape[1]
+        ws = torch.empty(max(m, 1), dtype=torch.float32, device=logits.device)
+        loss = torch.empty(1, dtype=torch.float32, device=logits.device)
+        nat.check(L.gnntf_node_xent_f32(nat.ptr(logits), _ld(logits), nat.ptr(nodes), nat.ptr(labels), m, C, nat.ptr(ws),
+                                        nat.ptr(loss), nat.stream_ptr()), "node_xent")
+        ctx.save_for_backward(logits, nodes, labels)
+        return loss.reshape(())
+
+    @staticmethod
+    def backward(ctx, g):
+        L = nat.lib()
+        logits, nodes, labels = ctx.saved_tensors
+        m, C = int(nodes.numel()), logits.shape[1]
+        d = torch.zeros_like(logits)
+        gs = g.reshape(1).to(torch.float32).contiguous()
+        nat.check(L.gnntf_node_xent_bwd_f32(nat.ptr(logits), _ld(logits), nat.ptr(nodes), nat.ptr(labels), m, C, nat.ptr(gs),
+                                            nat.ptr(d), _ld(d), nat.stream_ptr()), "node_xent_bwd")
+        return d, None, None
+
+
+def node_cross_entropy(logits, nodes, labels):
+    """``NodeClassification.loss`` (graph_predictor.py:19-25): gather + log-softmax + sparse CE, mean over
+    ``nodes`` — one kernel forward, one backward.  ``nodes``/``labels``: int64 CUDA tensors."""
+    C = logits.shape[1]
+    if labels.numel() and (int(labels.min()) < 0 or int(labels.max()) >= C):
+        raise Exception("labels out of range")
+    return _NodeXent.apply(logits, nodes.contiguous(), labels.contiguous())

@@ -58,6 +58,7 @@ extern "C" {
 /* activation fused in the step epilogue (PPRIteration activation, filter.py:22) */
 #define GNNTF_ACT_IDENTITY 0
 #define GNNTF_ACT_RELU 1
+#define GNNTF_ACT_LEAKY_RELU 2 /* gnntf_bias_act_dropout* only (NGCFLayer, gcn.py:117) */
 
 int gnntf_abi_version(void);
 const char* gnntf_status_str(int code);
@@ -195,6 +196,35 @@ int gnntf_appnp_propagate_bwd_f32(const gnntf_csr_t* AT_k, int K, const float* d
 int gnntf_appnp_propagate_host_f32(const gnntf_csr_t* A, const float* H0_host, float* out_host,
                                    float* dev_H0, float* dev_out, float* dev_scratch, int64_t ld,
                                    int64_t F, double alpha, int K, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * The element-wise stages on either side of the path, fused (callers of the propagation).
+ *
+ * gnntf_bias_act_dropout_f32: out = keep ∘ p_scale ∘ act(Z + bias) — the tail of Dense.__forward__
+ * (gnntf/core/nn/layers.py:135-136) and of GCNLayer.__forward__ (gcn.py:89) after the GEMM, one pass.
+ * bias: [F] or NULL; keep: uint8 [n,F] dense or NULL; slope: leaky-relu negative slope.  out may alias Z.
+ * gnntf_bias_act_dropout_bwd_f32: dZ = g ∘ keep ∘ p_scale ∘ act'(·) with act' taken from the forward
+ * OUTPUT y (not needed for GNNTF_ACT_IDENTITY); the bias gradient is the column sum of dZ (caller).
+ *
+ * gnntf_node_xent_f32: NodeClassification.loss (gnntf/core/gnn/graph_predictor.py:19-25) —
+ * mean_i [ logsumexp(logits[nodes[i],:]) − logits[nodes[i], labels[i]] ]; tf.nn.embedding_lookup,
+ * log_softmax and SparseCategoricalCrossentropy(from_logits=True) in one kernel (log_softmax is
+ * idempotent, so applying the loss to log-probabilities as the reference does gives the same value).
+ * per_node_ws: m floats of workspace; loss: 1 float.  The reduction order is fixed (deterministic).
+ * gnntf_node_xent_bwd_f32: dlogits[nodes[i],:] += grad_loss·(softmax − onehot)/m into a caller-zeroed
+ * [N,C] matrix (float atomics: bitwise reproducible when no node is listed twice).
+ * ---------------------------------------------------------------------------------------- */
+int gnntf_bias_act_dropout_f32(const float* Z, int64_t ldz, const float* bias, const uint8_t* keep,
+                               float p_scale, int activation, float slope, float* out, int64_t ldo,
+                               int64_t n, int64_t F, void* stream);
+int gnntf_bias_act_dropout_bwd_f32(const float* g, int64_t ldg, const float* y, int64_t ldy,
+                                   const uint8_t* keep, float p_scale, int activation, float slope,
+                                   float* dZ, int64_t ldd, int64_t n, int64_t F, void* stream);
+int gnntf_node_xent_f32(const float* logits, int64_t ld, const int64_t* nodes, const int64_t* labels,
+                        int64_t m, int64_t C, float* per_node_ws, float* loss, void* stream);
+int gnntf_node_xent_bwd_f32(const float* logits, int64_t ld, const int64_t* nodes, const int64_t* labels,
+                            int64_t m, int64_t C, const float* grad_loss, float* dlogits, int64_t ldd,
+                            void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Row-sharded multi-GPU helper (contiguous node-range split; BASELINE north_star).

@@ -265,6 +265,80 @@ def gcn_forward(indices, raw_values, n, X, weights, biases, dtype=F32):
     return H
 
 
+def leaky_relu(x, alpha=0.2):
+    """``tf.nn.leaky_relu`` (default alpha 0.2; NGCFLayer's default activation, gcn.py:117)."""
+    return np.where(x > 0, x, x * np.asarray(alpha, dtype=x.dtype))
+
+
+def l2_normalize(x, eps=1e-12):
+    """``tf.math.l2_normalize(x, axis=1)`` = x * rsqrt(max(sum(x**2), eps))  (gcn.py:135, gnn.py:23)."""
+    return x / np.sqrt(np.maximum((x * x).sum(axis=1, keepdims=True), np.asarray(eps, dtype=x.dtype)))
+
+
+def gcnii_layer(indices, norm_values, X, H0, W, a, l, k, activation=relu, bias=None, dtype=F32):
+    """``GCNIILayer.__forward__`` (gcn.py:22-27) in eval mode: b = log1p(l/(k+1)) (:23);
+    tradeoff = (1-a)·(Â·X) + a·H0 (:24-25); act(tradeoff · ((1-b)·I + b·W)) (:26-27).  With ``bias`` it is the
+    spectral-preserving variant (gcn.py:46-51): 2·(act(... + bias) − bias)."""
+    t = np.dtype(dtype).type
+    b = t(np.log1p(l / (k + 1)))
+    agg = spmm_coo(indices, norm_values, X, dtype=dtype)
+    tradeoff = t(1 - a) * agg + t(a) * np.asarray(H0).astype(dtype)
+    M = (t(1) - b) * np.eye(W.shape[1], dtype=dtype) + b * np.asarray(W).astype(dtype)
+    z = tradeoff @ M
+    if bias is not None:
+        bias = np.asarray(bias).astype(dtype)
+        return t(2) * (activation(z + bias) - bias)
+    return activation(z)
+
+
+def gcnii_forward(indices, raw_values, n, X, dense_w, dense_b, conv_w, out_w, out_b, a=0.1, l=0.5, conv_bias=None,
+                  dtype=F32):
+    """Eval-mode ``GCNII`` (gcn.py:54-74): Dense(relu) stack → H0 → len(conv_w) GCNIILayers (relu) →
+    Dense(num_classes).  All dropouts are identities in eval mode (layered.py:45,48)."""
+    idx, nv, _ = get_adjacency(indices, raw_values, n, "symmetric", "none", dtype=dtype)
+    H = np.asarray(X).astype(dtype)
+    for W, b in zip(dense_w, dense_b):
+        H = relu(H @ np.asarray(W).astype(dtype) + np.asarray(b).astype(dtype))
+    H0 = H
+    for k, W in enumerate(conv_w):
+        H = gcnii_layer(idx, nv, H, H0, W, a, l, k, relu, None if conv_bias is None else conv_bias[k], dtype=dtype)
+    return H @ np.asarray(out_w).astype(dtype) + np.asarray(out_b).astype(dtype)
+
+
+def ngcf_layer(indices, bip_values, X, W1, b1, W2, b2, activation=leaky_relu, dtype=F32):
+    """``NGCFLayer.__forward__`` (gcn.py:130-135), eval mode, with the bipartite-normalised adjacency of
+    :127 given: agg = Â·X; l2_normalize(act((X∘agg)·W1 + b1) + act(agg·W2 + b2))."""
+    X = np.asarray(X).astype(dtype)
+    agg = spmm_coo(indices, bip_values, X, dtype=dtype)
+    out = activation((X * agg) @ np.asarray(W1).astype(dtype) + np.asarray(b1).astype(dtype)) \
+        + activation(agg @ np.asarray(W2).astype(dtype) + np.asarray(b2).astype(dtype))
+    return l2_normalize(out)
+
+
+def ngcf_forward(indices, raw_values, n, X, layers, dtype=F32):
+    """Eval-mode ``NGCF`` (gcn.py:138-153): the NGCFLayers in sequence, then ``Concatenate`` of their
+    values — along axis 0, as layers.py:100 does.  ``layers``: list of (W1, b1, W2, b2)."""
+    idx, bv, _ = get_adjacency(indices, raw_values, n, "bipartite", "none", dtype=dtype)
+    H, values = np.asarray(X).astype(dtype), []
+    for (W1, b1, W2, b2) in layers:
+        H = ngcf_layer(idx, bv, H, W1, b1, W2, b2, dtype=dtype)
+        values.append(H)
+    return np.concatenate(values, axis=0)
+
+
+def node_classification_loss(logits, nodes, labels, dtype=F32):
+    """``NodeClassification.loss`` (graph_predictor.py:19-25): log_softmax of the looked-up rows, then
+    SparseCategoricalCrossentropy(from_logits=True) on those log-probabilities, mean over the nodes."""
+    rows = np.asarray(logits).astype(dtype)[np.asarray(nodes)]
+
+    def log_softmax(x):
+        m = x.max(axis=1, keepdims=True)
+        return x - m - np.log(np.exp(x - m).sum(axis=1, keepdims=True))
+    pred = log_softmax(rows)
+    ce = -log_softmax(pred)[np.arange(rows.shape[0]), np.asarray(labels)]
+    return ce.mean(dtype=dtype)
+
+
 # --------------------------------------------------------------------------------------
 # Derived CSR view (what the GPU builder must reproduce bit-exactly)
 # --------------------------------------------------------------------------------------

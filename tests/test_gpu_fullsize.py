@@ -174,7 +174,7 @@ def test_pubmed_gcn_training_forward_and_backward_vs_oracle():
     feat_keep_t = torch.from_numpy(feat_keep).cuda()
     arch.training_mode(True)
     arch.sparse_dropout = lambda G, p=0.5: G if p == 0 else MaskedAdjacency(G, edge_keep_t, float(p))
-    arch.dropout = lambda feats, p=0.5: feats if p == 0 else feats * feat_keep_t.to(feats.dtype) * float(oracle.dropout_scale(p))
+    arch.dropout_mask = lambda shape, p, device=None: None if p == 0 else feat_keep_t     # every feature dropout of the stack
     out = arch(arch.features)
     out.backward(torch.from_numpy(g_out).cuda())
     ws = arch.vars()

@@ -707,3 +707,172 @@ def test_arrange_sweep_kernel_vs_numpy():
     diff = np.minimum(diff, 2 * np.pi - diff)               # compare on the circle
     assert diff.max() < 2e-5, diff.max()
     assert np.array_equal(_np(out)[n - 5:], theta[n - 5:])
+
+
+# ------------------------------------------------------------------------------------------
+# §8 f-1 / f-2: fused dense tail, cached Â·X, fused node-classification loss
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("act", ["identity", "relu", "leaky_relu"])
+@pytest.mark.parametrize("F", [3, 64, 100])
+def test_bias_act_dropout_forward_and_backward_vs_numpy(act, F):
+    gnntf = _gnntf()
+    rng = np.random.default_rng(F)
+    n = 301
+    Z = rng.standard_normal((n, F)).astype(np.float32)
+    b = rng.standard_normal((1, F)).astype(np.float32)
+    keep = rng.random((n, F)) >= 0.4
+    g = rng.standard_normal((n, F)).astype(np.float32)
+    f = {"identity": lambda x: x, "relu": oracle.relu, "leaky_relu": oracle.leaky_relu}[act]
+    pre = Z + b
+    scale = oracle.dropout_scale(0.4)
+    expect = np.where(keep, f(pre) * scale, np.float32(0)).astype(np.float32)
+    Zt = torch.from_numpy(Z).cuda().requires_grad_(True)
+    bt = torch.from_numpy(b).cuda().requires_grad_(True)
+    out = gnntf.bias_act_dropout(Zt, bt, act, torch.from_numpy(keep).cuda(), 0.4)
+    assert np.array_equal(_np(out), expect)                       # same operations, same roundings
+    out.backward(torch.from_numpy(g).cuda())
+    slope = {"identity": np.ones_like(pre), "relu": (pre > 0).astype(np.float32),
+             "leaky_relu": np.where(pre > 0, 1.0, 0.2).astype(np.float32)}[act]
+    dZ = g * keep * scale * slope
+    oracle.assert_close(_np(Zt.grad), dZ, what=f"dZ {act}")
+    oracle.assert_close(_np(bt.grad), dZ.sum(0, keepdims=True), what=f"dbias {act}", floor=oracle.FLOOR_REORDERED)
+    # no dropout, no bias
+    out2 = gnntf.bias_act_dropout(torch.from_numpy(Z).cuda(), None, act)
+    assert np.array_equal(_np(out2), f(Z))
+
+
+def test_node_cross_entropy_vs_oracle_and_torch():
+    gnntf = _gnntf()
+    rng = np.random.default_rng(3)
+    n, C, m = 5000, 47, 1234
+    logits = (rng.standard_normal((n, C)) * 3).astype(np.float32)
+    nodes = rng.choice(n, m, replace=False).astype(np.int64)
+    labels = rng.integers(0, C, m).astype(np.int64)
+    lt = torch.from_numpy(logits).cuda().requires_grad_(True)
+    task = gnntf.NodeClassification(nodes, labels)
+    loss = task.loss(lt)
+    expect = oracle.node_classification_loss(logits.astype(np.float64), nodes, labels, dtype=np.float64)
+    assert abs(float(loss) - float(expect)) <= 1e-5 * abs(float(expect))
+    loss.backward()
+    ref = torch.from_numpy(logits).cuda().requires_grad_(True)
+    rows = ref.index_select(0, torch.from_numpy(nodes).cuda())
+    torch.nn.functional.cross_entropy(torch.log_softmax(rows, 1), torch.from_numpy(labels).cuda()).backward()
+    oracle.assert_close(_np(lt.grad), _np(ref.grad), what="node CE gradient", floor=oracle.FLOOR_REORDERED)
+    assert task.evaluate(lt.detach()) == pytest.approx(float((logits[nodes].argmax(1) == labels).mean()))
+
+
+def test_gcn_first_layer_aggregation_is_cached_in_eval_mode():
+    gnntf = _gnntf()
+    gnntf.set_seed(2)
+    n, e, width, classes = 400, 2400, 30, 4
+    G = synthetic.citation_graph(n, e, seed=8)
+    X = synthetic.citation_features(n, width, seed=9)
+    arch = gnntf.GCN(gnntf.graph2adj(G), X, num_classes=classes, latent_dims=[48])   # widening layer: (ÂX)W order
+    arch.reset()
+    arch.training_mode(False)
+    out1 = arch(arch.features)
+    A = arch.get_adjacency(0)
+    assert getattr(A, "_agg_cache", None) is not None and A._agg_cache[0] is arch.features
+    calls = []
+    orig = gnntf.ops.sparse_dense_matmul
+    gnntf.gnn.ops.sparse_dense_matmul = lambda a, h: (calls.append(h.shape), orig(a, h))[1]
+    try:
+        out2 = arch(arch.features)
+    finally:
+        gnntf.gnn.ops.sparse_dense_matmul = orig
+    assert torch.equal(out1, out2) and calls == [(n, 4)], calls   # only the second layer propagates (at its output width)
+    Ws = [w.numpy() for w in arch.vars()][0::2]
+    bs = [w.numpy() for w in arch.vars()][1::2]
+    idx, val, _ = oracle.graph2adj(G)
+    oracle.assert_close(_np(out1), oracle.gcn_forward(idx, val, n, X, Ws, bs), what="GCN (cached ÂX) eval forward")
+
+
+# ------------------------------------------------------------------------------------------
+# §8 f-4: GCNII / NGCF / spectral-preserving variants / Structural on the same op
+# ------------------------------------------------------------------------------------------
+def _small_graph(seed, n=500, e=2600, width=40):
+    G = synthetic.citation_graph(n, e, seed=seed)
+    X = synthetic.citation_features(n, width, seed=seed + 1)
+    return G, X, n
+
+
+@pytest.mark.parametrize("spectral", [False, True])
+def test_gcnii_eval_forward_vs_oracle(spectral):
+    gnntf = _gnntf()
+    gnntf.set_seed(4)
+    G, X, n = _small_graph(11)
+    layer_type = gnntf.GCNIISpectralPreservingLayer if spectral else gnntf.GCNIILayer
+    arch = gnntf.GCNII(gnntf.graph2adj(G), X, num_classes=5, latent_dims=[32], iterations=8, layer_type=layer_type)
+    arch.reset()
+    rng = np.random.default_rng(0)
+    for layer in arch.layers():          # the reference initialises the convolution weights to zero (gcn.py:11): perturb them
+        if isinstance(layer, gnntf.GCNIILayer):
+            layer.W.data.copy_(torch.from_numpy((rng.standard_normal(tuple(layer.W.shape)) * 0.2).astype(np.float32)))
+            if spectral:
+                layer.bias.data.copy_(torch.from_numpy((rng.standard_normal(tuple(layer.bias.shape)) * 0.1).astype(np.float32)))
+    arch.training_mode(False)
+    out = _np(arch(arch.features))
+    layers = arch.layers()
+    dense = [l for l in layers if isinstance(l, gnntf.Dense)]
+    conv = [l for l in layers if isinstance(l, gnntf.GCNIILayer)]
+    assert len(conv) == 8 and [c.k for c in conv] == list(range(8))
+    idx, val, _ = oracle.graph2adj(G)
+    expect = oracle.gcnii_forward(idx, val, n, X, [_np(dense[0].W)], [_np(dense[0].b)], [_np(c.W) for c in conv],
+                                  _np(dense[1].W), _np(dense[1].b), a=0.1, l=0.5,
+                                  conv_bias=[_np(c.bias) for c in conv] if spectral else None)
+    oracle.assert_close(out, expect, what=f"GCNII eval forward spectral={spectral}", floor=oracle.FLOOR_REORDERED)
+
+
+def test_gcnii_training_step_runs_and_gradients_reach_every_variable():
+    gnntf = _gnntf()
+    gnntf.set_seed(5)
+    G, X, n = _small_graph(13)
+    arch = gnntf.GCNII(gnntf.graph2adj(G), X, num_classes=4, latent_dims=[16], iterations=4)
+    labels = np.random.default_rng(1).integers(0, 4, n)
+    arch.train(gnntf.NodeClassification(np.arange(0, 200), labels[:200]), gnntf.NodeClassification(np.arange(200, 300), labels[200:300]),
+               epochs=3, patience=3)
+    assert all(torch.isfinite(w.var).all() for w in arch.vars())
+    assert any(float(w.var.abs().sum()) > 0 for w in arch.vars() if w.normalization == "zero" and w.var.shape[0] == w.var.shape[1])
+
+
+def test_ngcf_eval_forward_vs_oracle():
+    gnntf = _gnntf()
+    gnntf.set_seed(6)
+    G, X, n = _small_graph(15, width=12)
+    arch = gnntf.NGCF(gnntf.graph2adj(G), X, num_classes=12, dropout=0.1)
+    arch.reset()
+    arch.training_mode(False)
+    out = _np(arch(arch.features))
+    assert out.shape == (3 * n, 12)                        # Concatenate stacks along axis 0 (layers.py:100)
+    ng = [l for l in arch.layers() if isinstance(l, gnntf.NGCFLayer)]
+    assert len(ng) == 3 and all(l.adjacency.mode == "bipartite" for l in ng)
+    idx, val, _ = oracle.graph2adj(G)
+    expect = oracle.ngcf_forward(idx, val, n, X, [(_np(l.W1), _np(l.b1), _np(l.W2), _np(l.b2)) for l in ng])
+    oracle.assert_close(out, expect, what="NGCF eval forward", floor=oracle.FLOOR_REORDERED)
+    rows = np.linalg.norm(out, axis=1)
+    assert np.allclose(rows[rows > 0], 1.0, atol=1e-5)     # l2_normalize (gcn.py:135)
+
+
+def test_gcn_spectral_preserving_layer_and_structural_preprocessor():
+    gnntf = _gnntf()
+    gnntf.set_seed(7)
+    G, X, n = _small_graph(17, width=10)
+    arch = gnntf.GCN(gnntf.graph2adj(G), X, num_classes=3, latent_dims=[16], layer_type=gnntf.GCNSpectralPreservingLayer,
+                     preprocessor=gnntf.Structural(dims=6))
+    arch.reset()
+    with torch.no_grad():
+        for w in arch.vars():
+            if w.var.shape[0] == 1:
+                w.var.uniform_(-0.3, 0.3)                   # non-zero biases so that the "- b" term matters
+    arch.training_mode(False)
+    out = _np(arch(arch.features))
+    st = arch.layers()[0]
+    assert isinstance(st, gnntf.Structural) and st.output_shape == (n, 16)
+    Xp = np.concatenate([_np(st.embeddings2), X], axis=1)
+    idx, val, _ = oracle.graph2adj(G)
+    _, nv, _ = oracle.get_adjacency(idx, val, n)
+    H = Xp.astype(np.float32)
+    for layer in arch.layers()[1:]:
+        W, b = _np(layer.W), _np(layer.b)
+        H = 2 * (oracle.relu(oracle.spmm_coo(idx, nv, H) @ W + b) - b)       # gcn.py:104-105, eval mode
+    oracle.assert_close(out, H, what="GCN spectral-preserving + Structural", floor=oracle.FLOOR_REORDERED)

@@ -232,3 +232,39 @@ def test_big_oracle_csr_route_is_bit_identical_to_the_coo_loop(F):
     # and against the NumPy oracle within the fp32 tolerance
     oracle.assert_close(out, oracle.appnp_propagate(big.idx, big.raw, n, H0, a, K)[-1], what="C vs NumPy K=10")
     assert np.array_equal(big.step(H0, H0, a), big.propagate(H0, a, 1))
+
+
+def test_oracle_variant_layers_against_dense_algebra():
+    """GCNII / NGCF / loss restatements against the same formulas written with a dense adjacency."""
+    rng = np.random.default_rng(5)
+    n, F = 60, 7
+    edges, w = _random_graph(n, 400, 3)
+    idx, val, _ = oracle.graph2adj_arrays(edges, w, n)
+    _, nv, _ = oracle.get_adjacency(idx, val, n, dtype=np.float64)
+    A = np.zeros((n, n))
+    np.add.at(A, (idx[:, 0], idx[:, 1]), nv)
+    X, H0 = rng.standard_normal((n, F)), rng.standard_normal((n, F))
+    W = rng.standard_normal((F, F)) * 0.3
+    got = oracle.gcnii_layer(idx, nv, X, H0, W, 0.1, 0.5, 2, dtype=np.float64)
+    b = np.log1p(0.5 / 3)
+    np.testing.assert_allclose(got, np.maximum((0.9 * A @ X + 0.1 * H0) @ ((1 - b) * np.eye(F) + b * W), 0), rtol=1e-12, atol=1e-12)
+    bias = rng.standard_normal((1, F)) * 0.1
+    got = oracle.gcnii_layer(idx, nv, X, H0, W, 0.1, 0.5, 2, bias=bias, dtype=np.float64)
+    np.testing.assert_allclose(got, 2 * (np.maximum((0.9 * A @ X + 0.1 * H0) @ ((1 - b) * np.eye(F) + b * W) + bias, 0) - bias),
+                               rtol=1e-12, atol=1e-12)
+    _, bv, _ = oracle.get_adjacency(idx, val, n, "bipartite", dtype=np.float64)
+    Ab = np.zeros((n, n))
+    np.add.at(Ab, (idx[:, 0], idx[:, 1]), bv)
+    W1, W2 = rng.standard_normal((F, 4)), rng.standard_normal((F, 4))
+    b1, b2 = rng.standard_normal((1, 4)), rng.standard_normal((1, 4))
+    got = oracle.ngcf_layer(idx, bv, X, W1, b1, W2, b2, dtype=np.float64)
+    agg = Ab @ X
+    lr = lambda z: np.where(z > 0, z, 0.2 * z)  # noqa: E731
+    ref = lr((X * agg) @ W1 + b1) + lr(agg @ W2 + b2)
+    np.testing.assert_allclose(got, ref / np.linalg.norm(ref, axis=1, keepdims=True), rtol=1e-10, atol=1e-12)
+    logits = rng.standard_normal((n, 5))
+    nodes, labels = np.arange(0, 20), rng.integers(0, 5, 20)
+    rows = logits[nodes]
+    lse = np.log(np.exp(rows).sum(1))
+    np.testing.assert_allclose(oracle.node_classification_loss(logits, nodes, labels, dtype=np.float64),
+                               (lse - rows[np.arange(20), labels]).mean(), rtol=1e-12)
