@@ -299,7 +299,7 @@ def gpu_arm(args):
         H0_local = (H0 if adj.perm is None else H0.index_select(0, adj.perm))[prop.lo:prop.hi, c0:c1].contiguous()
         run = lambda: prop.propagate(H0_local, ALPHA, K_ITER)  # noqa: E731
         launches_per_step = prop.launches_per_propagation(K_ITER)
-        how = ("fused pack+send over NVLink peer memory + one-element NCCL all-reduce as barrier" if prop.push
+        how = ("fused pack+send+signal kernel over NVLink peer memory, epoch flags acquired on the device" if prop.push
                else "pack kernel + NCCL all-to-all")
         sharding = (f"{R} row groups (contiguous node ranges balanced by nnz; halo rows by {how}, inside a column "
                     f"group) x {C} feature-column groups (no communication)")
@@ -390,11 +390,15 @@ def gpu_arm(args):
                          "d2h_bytes_per_step": n * F * 4, "ms_per_step": e2e_s * 1e3,
                          "api": "gnntf.appnp_propagate_host -> gnntf_appnp_propagate_host_f32 (pinned host H0 in, host H_K out)"}
     else:
-        e2e = prop.propagate_host_timed(ALPHA, K_ITER, reps=max(1, min(args.steps, 3)))
+        # the REAL shard of H0 goes host -> device, the result shard comes back and is compared with the device run
+        e2e = prop.propagate_host_timed(H0_local.cpu(), ALPHA, K_ITER, reps=max(1, min(args.steps, 3)))
+        same = torch.tensor([1.0 if torch.equal(e2e["host_out"], run().cpu()) else 0.0], device=dev)
+        torch.distributed.all_reduce(same, op=torch.distributed.ReduceOp.MIN)
         if rank == 0:
             result["e2e"] = {"value": nnz * F * K_ITER / e2e["seconds"], "unit": UNIT,
                              "h2d_bytes_per_step": e2e["h2d"], "d2h_bytes_per_step": e2e["d2h"],
-                             "ms_per_step": e2e["seconds"] * 1e3, "api": "gnntf.dist.ShardedPropagator.propagate_host"}
+                             "ms_per_step": e2e["seconds"] * 1e3, "api": "gnntf.dist.ShardedPropagator.propagate_host_timed",
+                             "host_result_equals_device_run_on_every_rank": bool(same.item() > 0)}
 
     # ---- parity of the timed propagation against the C oracle (every N), then the CPU baseline --------
     big = None

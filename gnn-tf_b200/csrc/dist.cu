@@ -29,11 +29,49 @@ __global__ void halo_pack_kernel(const float* __restrict__ H, int64_t ld, const 
 // row (G sized to the row width), a warp runs 32/G rows side by side and every group keeps U rows
 // in flight (index loads, then all row loads, then all remote stores): the first version — one warp
 // per row, one row at a time — was latency-bound at 233 GB/s (profiles/r1, N=8 phase timing).
+__device__ __forceinline__ void st_release_sys(int32_t* p, int32_t v) {
+    asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ int32_t ld_acquire_sys(const int32_t* p) {
+    int32_t v;
+    asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// Completion signal of a push (all arguments NULL/0 = no signalling).  Every CTA fences its remote
+// stores at system scope and counts itself in; the LAST one publishes `*epoch_base + epoch_delta` into
+// slot `my_slot` of every destination's flag array with a release store over NVLink, so a consumer
+// that acquires the flag also sees every row this rank pushed (and the counter is left at zero for
+// the next launch).  This replaces the host-issued NCCL all-reduce round 1 used as the barrier.
+struct PushSignal {
+    int32_t* done_counter;              // local, zero between launches
+    int32_t* const* peer_flags;         // [n_peers] flag arrays of the peers (peer memory), NULL entries skipped
+    const int32_t* epoch_base;          // device scalar advanced by the host side once per propagation
+    int32_t epoch_delta;
+    int32_t my_slot;
+};
+
+__device__ __forceinline__ void push_signal_tail(const PushSignal& sg, int n_peers) {
+    if (sg.done_counter == nullptr) return;
+    __threadfence_system();             // this thread's remote stores are performed before its CTA is counted
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const int prev = atomicAdd(sg.done_counter, 1);
+        if (prev == (int)gridDim.x - 1) {
+            __threadfence_system();     // order the other CTAs' (fenced, counted) stores before the flags
+            const int32_t epoch = *sg.epoch_base + sg.epoch_delta;
+            for (int d = 0; d < n_peers; ++d)
+                if (sg.peer_flags[d] != nullptr) st_release_sys(sg.peer_flags[d] + sg.my_slot, epoch);
+            *sg.done_counter = 0;
+        }
+    }
+}
+
 template <int VEC, int G, int U>
 __global__ void halo_push_kernel(const float* __restrict__ H, int64_t ld, const int32_t* __restrict__ send_idx,
                                  const int64_t* __restrict__ send_off, float* const* __restrict__ peer_base,
                                  const int64_t* __restrict__ peer_row0, int n_peers, int64_t n_send,
-                                 int64_t rotate, int64_t ldo, int F) {
+                                 int64_t rotate, int64_t ldo, int F, PushSignal sg) {
     constexpr int RPW = 32 / G;
     const int lane = threadIdx.x & 31;
     const int gl = lane % G;
@@ -72,6 +110,33 @@ __global__ void halo_push_kernel(const float* __restrict__ H, int64_t ld, const 
                     for (int f = gl * VEC; f < F; f += G * VEC) Vec<VEC>::gather(src[u] + f).store(dst[u] + f);
         }
     }
+    push_signal_tail(sg, n_peers);
+}
+
+// Spin (one warp) until flags[i] >= *epoch_base + epoch_delta for every i != skip.  Enqueued on the
+// consumer's stream in front of the kernel that reads the pushed rows: the acquire pairs with the
+// producers' release stores; the kernel boundary orders it before the consumer's loads.  A peer that
+// never arrives traps after ~4 s instead of hanging the GPU.
+__global__ void wait_flags_kernel(const int32_t* __restrict__ flags, int n, int skip, const int32_t* __restrict__ epoch_base,
+                                  int32_t epoch_delta) {
+    const int32_t epoch = *epoch_base + epoch_delta;
+    const long long t0 = clock64();
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        if (i == skip) continue;
+        while (ld_acquire_sys(flags + i) - epoch < 0) {     // wrap-safe comparison
+            if (clock64() - t0 > 8000000000LL) __trap();
+            __nanosleep(100);
+        }
+    }
+}
+
+// flags_of_peer[d][my_slot] = *epoch_base + epoch_delta for every mapped peer (release): "this rank is
+// done reading its halo buffers of the propagation that just ended".
+__global__ void signal_flags_kernel(int32_t* const* __restrict__ peer_flags, int n_peers, int my_slot,
+                                    const int32_t* __restrict__ epoch_base, int32_t epoch_delta) {
+    const int32_t epoch = *epoch_base + epoch_delta;
+    for (int d = threadIdx.x; d < n_peers; d += blockDim.x)
+        if (peer_flags[d] != nullptr) st_release_sys(peer_flags[d] + my_slot, epoch);
 }
 
 }  // namespace gnntf
@@ -94,23 +159,22 @@ extern "C" int gnntf_halo_pack_f32(const float* H, int64_t ld, const int32_t* se
     return GNNTF_OK;
 }
 
-extern "C" int gnntf_halo_push_f32(const float* H, int64_t ld, const int32_t* send_idx, const int64_t* send_off,
-                                   float* const* peer_base, const int64_t* peer_row0, int n_peers,
-                                   int64_t n_send, int64_t rotate, int64_t ldo, int64_t F, void* stream) {
+static int halo_push_impl(const float* H, int64_t ld, const int32_t* send_idx, const int64_t* send_off,
+                          float* const* peer_base, const int64_t* peer_row0, int n_peers, int64_t n_send,
+                          int64_t rotate, int64_t ldo, int64_t F, PushSignal sg, cudaStream_t st) {
     if (n_send < 0 || F < 0 || F > 0x7fffffff || ld < F || ldo < F || n_peers < 1 || n_peers > 64) return GNNTF_E_SIZE;
     if (rotate < 0 || (n_send > 0 && rotate >= n_send)) return GNNTF_E_SIZE;
-    if (n_send == 0 || F == 0) return GNNTF_OK;
-    if (H == nullptr || send_idx == nullptr || send_off == nullptr || peer_base == nullptr || peer_row0 == nullptr)
+    if (F == 0 || (n_send == 0 && sg.done_counter == nullptr)) return GNNTF_OK;
+    if (n_send > 0 && (H == nullptr || send_idx == nullptr || send_off == nullptr || peer_base == nullptr || peer_row0 == nullptr))
         return GNNTF_E_NULL;
     // The push overlaps the owned-column SpMM pass: a small grid leaves the SMs to that kernel
     // (NVLink needs far fewer warps in flight than HBM does).
     const int max_ctas = kNumSMs;
-    const int grid = (int)std::min<int64_t>(ceil_div(n_send, 8), (int64_t)max_ctas);
+    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div(n_send, 8), (int64_t)max_ctas));  // >= 1: the signal must go out
     const bool v4 = (F % 4 == 0) && (ld % 4 == 0) && (ldo % 4 == 0) && (reinterpret_cast<uintptr_t>(H) & 15u) == 0;
-    cudaStream_t st = (cudaStream_t)stream;
 #define GNNTF_PUSH(VEC, G)                                                                                     \
     halo_push_kernel<VEC, G, 4><<<grid, 256, 0, st>>>(H, ld, send_idx, send_off, peer_base, peer_row0, n_peers, \
-                                                      n_send, rotate, ldo, (int)F)
+                                                      n_send, rotate, ldo, (int)F, sg)
     if (v4) {
         if (F <= 16) GNNTF_PUSH(4, 4);
         else if (F <= 32) GNNTF_PUSH(4, 8);
@@ -122,6 +186,44 @@ extern "C" int gnntf_halo_push_f32(const float* H, int64_t ld, const int32_t* se
         else GNNTF_PUSH(1, 32);
     }
 #undef GNNTF_PUSH
+    GNNTF_LAUNCH_CHECK();
+    return GNNTF_OK;
+}
+
+extern "C" int gnntf_halo_push_f32(const float* H, int64_t ld, const int32_t* send_idx, const int64_t* send_off,
+                                   float* const* peer_base, const int64_t* peer_row0, int n_peers,
+                                   int64_t n_send, int64_t rotate, int64_t ldo, int64_t F, void* stream) {
+    return halo_push_impl(H, ld, send_idx, send_off, peer_base, peer_row0, n_peers, n_send, rotate, ldo, F, PushSignal{},
+                          (cudaStream_t)stream);
+}
+
+extern "C" int gnntf_halo_push_signal_f32(const float* H, int64_t ld, const int32_t* send_idx, const int64_t* send_off,
+                                          float* const* peer_base, const int64_t* peer_row0, int n_peers,
+                                          int64_t n_send, int64_t rotate, int64_t ldo, int64_t F,
+                                          int32_t* done_counter, int32_t* const* peer_flags, int my_slot,
+                                          const int32_t* epoch_base, int32_t epoch_delta, void* stream) {
+    if (done_counter == nullptr || peer_flags == nullptr || epoch_base == nullptr) return GNNTF_E_NULL;
+    if (my_slot < 0) return GNNTF_E_SIZE;
+    return halo_push_impl(H, ld, send_idx, send_off, peer_base, peer_row0, n_peers, n_send, rotate, ldo, F,
+                          PushSignal{done_counter, peer_flags, epoch_base, epoch_delta, my_slot}, (cudaStream_t)stream);
+}
+
+extern "C" int gnntf_flags_wait(const int32_t* flags, int n, int skip, const int32_t* epoch_base, int32_t epoch_delta,
+                                void* stream) {
+    if (n < 0 || n > 1024) return GNNTF_E_SIZE;
+    if (n == 0) return GNNTF_OK;
+    if (flags == nullptr || epoch_base == nullptr) return GNNTF_E_NULL;
+    wait_flags_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(flags, n, skip, epoch_base, epoch_delta);
+    GNNTF_LAUNCH_CHECK();
+    return GNNTF_OK;
+}
+
+extern "C" int gnntf_flags_signal(int32_t* const* peer_flags, int n_peers, int my_slot, const int32_t* epoch_base,
+                                  int32_t epoch_delta, void* stream) {
+    if (n_peers < 0 || n_peers > 1024 || my_slot < 0) return GNNTF_E_SIZE;
+    if (n_peers == 0) return GNNTF_OK;
+    if (peer_flags == nullptr || epoch_base == nullptr) return GNNTF_E_NULL;
+    signal_flags_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(peer_flags, n_peers, my_slot, epoch_base, epoch_delta);
     GNNTF_LAUNCH_CHECK();
     return GNNTF_OK;
 }

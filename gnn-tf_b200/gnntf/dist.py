@@ -196,19 +196,25 @@ def exchange_halo(plan: ShardPlan, send_buf, halo_out, group=None, async_op=Fals
                                   input_split_sizes=plan.send_counts, group=group, async_op=async_op)
 
 
-class _SharedMatrix:
-    """fp32 [rows, cols] device matrix allocated through gnntf_ipc_alloc so that peers can map it
-    (CUDA IPC) and store halo rows into it directly; exposed to torch without a copy."""
+class _SharedBuffer:
+    """Device allocation made through gnntf_ipc_alloc so that peers can map it (CUDA IPC) and store
+    into it directly; exposed to torch without a copy.  Freed by :meth:`free` (never by ``__del__``: a
+    peer may still have it mapped — ShardedPropagator.close() orders the teardown)."""
 
-    def __init__(self, rows, cols, device):
+    def __init__(self, shape, dtype, device):
         from . import _native as nat
-        self.nat, self.rows, self.cols = nat, int(rows), int(cols)
+        self.nat, self.shape = nat, tuple(int(x) for x in shape)
+        itemsize = torch.empty(0, dtype=dtype).element_size()
+        count = 1
+        for x in self.shape:
+            count *= x
         ptr = ctypes.c_void_p()
         self.handle = (ctypes.c_ubyte * 64)()
         with torch.cuda.device(device):
-            nat.check(nat.lib().gnntf_ipc_alloc(max(16, self.rows * self.cols * 4), ctypes.byref(ptr), self.handle), "ipc_alloc")
+            nat.check(nat.lib().gnntf_ipc_alloc(max(16, count * itemsize), ctypes.byref(ptr), self.handle), "ipc_alloc")
         self.ptr = ptr.value
-        self.__cuda_array_interface__ = {"shape": (self.rows, self.cols), "typestr": "<f4", "data": (self.ptr, False),
+        typestr = {torch.float32: "<f4", torch.int32: "<i4"}[dtype]
+        self.__cuda_array_interface__ = {"shape": self.shape, "typestr": typestr, "data": (self.ptr, False),
                                          "version": 2, "strides": None}
         self.tensor = torch.as_tensor(self, device=device)
         self.tensor.zero_()
@@ -216,11 +222,11 @@ class _SharedMatrix:
     def handle_bytes(self):
         return bytes(self.handle)
 
-    def __del__(self):
-        try:
-            self.nat.lib().gnntf_ipc_free(ctypes.c_void_p(self.ptr))
-        except Exception:
-            pass
+    def free(self):
+        if self.ptr:
+            self.tensor = None
+            self.nat.check(self.nat.lib().gnntf_ipc_free(ctypes.c_void_p(self.ptr)), "ipc_free")
+            self.ptr = 0
 
 
 class _EventWork:
@@ -234,21 +240,24 @@ class _EventWork:
 
 
 class ShardedPropagator:
-    """APPNP K-step propagation of one shard on one GPU (see module docstring).
+    """APPNP K-step propagation (and plain SpMM) of one shard on one GPU (see module docstring).
 
-    ``push`` (default): halo rows travel by the fused pack+send kernel over NVLink peer memory
-    (``gnntf_halo_push_f32``); if the peers' buffers cannot be mapped every rank falls back to the
-    NCCL all-to-all.  ``halves=2`` runs two independent chains over the two halves of the feature
-    columns, software-pipelined so one half's exchange is in flight while the other half computes —
-    kept for experiments, measured slower than the default."""
+    ``push`` (default): halo rows travel by the fused pack+send kernel over NVLink peer memory, and the
+    ranks synchronise through epoch flags in peer memory written by that same kernel
+    (``gnntf_halo_push_signal_f32``: st.release.sys after the rows; the consumer acquires them with
+    ``gnntf_flags_wait`` in front of the halo-column pass) — no collective and no host round trip
+    inside a propagation.  If the peers' buffers cannot be mapped every rank falls back to the NCCL
+    all-to-all.  ``peers="local"`` wires several propagators of ONE process to each other instead of
+    using CUDA IPC (single-GPU emulation of the ranks for tests: :func:`connect_local`,
+    :func:`propagate_lockstep`)."""
 
-    def __init__(self, adj, A, F, rank, world, group=None, plan=None, exchange=None, halves=None, push=True):
+    def __init__(self, adj, A, F, rank, world, group=None, plan=None, exchange=None, halves=None, push=True, peers="ipc"):
         from . import _native as nat
         from .sparse import CsrStructure
         self.nat = nat
         self.group, self.F = group, int(F)
         self._exchange = exchange  # test hook: single-process emulation of the all-to-all
-        self.comm_stream = torch.cuda.Stream(priority=-1) if (world > 1 and torch.cuda.is_available()) else None
+        self.comm_stream = torch.cuda.Stream(priority=-1) if (world > 1 and torch.cuda.is_available() and peers == "ipc") else None
         csr = A.csr
         self.plan = p = plan if plan is not None else build_shard_plan(csr.row_ptr, csr.col_idx, A.val, rank, world, group)
         self.lo, self.hi, self.n_local, self.n_halo = p.lo, p.hi, p.n_local, p.n_halo
@@ -267,9 +276,10 @@ class ShardedPropagator:
         n_ext, n_send = self.n_local + self.n_halo, int(sum(p.send_counts))
         self.push = bool(push) and p.world > 1 and exchange is None
         self.parts, col0, self._shared = [], 0, []
+        self._opened, self._flags, self._closed = [], None, False
         for w in widths:
             if self.push:
-                mats = [_SharedMatrix(n_ext, w, dev) for _ in range(2)]
+                mats = [_SharedBuffer((n_ext, w), torch.float32, dev) for _ in range(2)]
                 self._shared.append(mats)
                 bufs = [m.tensor for m in mats]
             else:
@@ -278,6 +288,11 @@ class ShardedPropagator:
                                    H0=torch.empty((self.n_local, w), dtype=torch.float32, device=dev), work=None))
             col0 += w
         if self.push:
+            # flags[0, q]: epoch of the last push received from rank q; flags[1, q]: rank q's end-of-propagation ack
+            self._flags = _SharedBuffer((2, p.world), torch.int32, dev)
+            self._epoch = torch.zeros(1, dtype=torch.int32, device=dev)
+            self._done = torch.zeros(1, dtype=torch.int32, device=dev)
+        if self.push and peers == "ipc":
             # every rank of the row group must take the same path: agree on whether IPC mapping worked
             try:
                 self._map_peers()
@@ -299,15 +314,15 @@ class ShardedPropagator:
             part["send"] = torch.empty((part["n_send"], part["F"]), dtype=torch.float32, device=part["H0"].device)
         return part["send"]
 
-    def _map_peers(self):
-        """Exchange IPC handles and halo layouts inside the row group and build, per part and per
-        ping-pong buffer, the device tables gnntf_halo_push_f32 needs."""
-        nat, L, p = self.nat, self.nat.lib(), self.plan
+    # -- peer tables ------------------------------------------------------------------------
+    def _layout(self):
+        return dict(recv_counts=list(self.plan.recv_counts), n_local=self.n_local)
+
+    def _build_tables(self, everyone, buffer_ptr, flags_ptr):
+        """Device tables the push kernel needs.  ``everyone[q]``: layout dict of rank q;
+        ``buffer_ptr(q, part, buf)`` / ``flags_ptr(q)``: addresses of rank q's buffers as seen from here."""
+        p = self.plan
         dev = p.row_ptr.device
-        mine = dict(handles=[[m.handle_bytes() for m in mats] for mats in self._shared],
-                    recv_counts=list(p.recv_counts), n_local=self.n_local)
-        everyone = [None] * p.world
-        dist.all_gather_object(everyone, mine, group=self.group)
         send_off = [0]
         for c in p.send_counts:
             send_off.append(send_off[-1] + int(c))
@@ -317,35 +332,99 @@ class ShardedPropagator:
         # my rows land in peer q's halo region after the rows of lower-ranked owners
         row0 = [int(everyone[q]["n_local"]) + int(sum(everyone[q]["recv_counts"][:p.rank])) for q in range(p.world)]
         self._peer_row0 = torch.tensor(row0, dtype=torch.int64, device=dev)
-        self._peer_ptrs, self._opened = [], []
+        self._peer_ptrs = []
         for pi in range(len(self.parts)):
             per_buf = []
             for bi in range(2):
-                ptrs = []
-                for q in range(p.world):
-                    if q == p.rank or p.send_counts[q] == 0:
-                        ptrs.append(0)
-                        continue
-                    h = (ctypes.c_ubyte * 64).from_buffer_copy(everyone[q]["handles"][pi][bi])
-                    out = ctypes.c_void_p()
-                    nat.check(L.gnntf_ipc_open(h, ctypes.byref(out)), "ipc_open")
-                    self._opened.append(out.value)
-                    ptrs.append(out.value)
+                ptrs = [0 if (q == p.rank or p.send_counts[q] == 0) else buffer_ptr(q, pi, bi) for q in range(p.world)]
                 per_buf.append(torch.tensor(ptrs, dtype=torch.int64, device=dev))
             self._peer_ptrs.append(per_buf)
-        self._flag = torch.zeros(1, dtype=torch.float32, device=dev)
+        # every peer gets my completion flags (also peers I send no rows to: they wait on all slots)
+        fl = [0 if q == p.rank else flags_ptr(q) for q in range(p.world)]
+        self._peer_data_flags = torch.tensor(fl, dtype=torch.int64, device=dev)
+        self._peer_ack_flags = torch.tensor([0 if x == 0 else x + 4 * p.world for x in fl], dtype=torch.int64, device=dev)
+
+    def _map_peers(self):
+        """Exchange IPC handles and halo layouts inside the row group and map the peers' buffers."""
+        nat, L, p = self.nat, self.nat.lib(), self.plan
+        mine = dict(self._layout(), handles=[[m.handle_bytes() for m in mats] for mats in self._shared],
+                    flags=self._flags.handle_bytes())
+        everyone = [None] * p.world
+        dist.all_gather_object(everyone, mine, group=self.group)
+
+        def open_handle(raw):
+            h = (ctypes.c_ubyte * 64).from_buffer_copy(raw)
+            out = ctypes.c_void_p()
+            nat.check(L.gnntf_ipc_open(h, ctypes.byref(out)), "ipc_open")
+            self._opened.append(out.value)
+            return out.value
+        self._build_tables(everyone, lambda q, pi, bi: open_handle(everyone[q]["handles"][pi][bi]),
+                           lambda q: open_handle(everyone[q]["flags"]))
+
+    def close(self):
+        """Tear the peer mappings down in a safe order: drain this GPU, barrier the group (nobody is still
+        storing into anybody's buffers), unmap the peers' allocations, barrier again, free our own.  Tensors
+        returned by :meth:`propagate` are views of these buffers and are invalid afterwards."""
+        if self._closed:
+            return
+        self._closed = True
+        if torch.cuda.is_available():
+            torch.cuda.synchronize()
+        multi = self.group is not None or (dist.is_available() and dist.is_initialized() and self.plan.world > 1
+                                           and self.comm_stream is not None)
+        if multi:
+            dist.barrier(group=self.group)
+        for ptr in self._opened:
+            self.nat.check(self.nat.lib().gnntf_ipc_close(ctypes.c_void_p(ptr)), "ipc_close")
+        self._opened = []
+        if multi:
+            dist.barrier(group=self.group)
+        for part in self.parts:
+            part["buf"] = None
+        self.buf = None
+        for mats in self._shared:
+            for m in mats:
+                m.free()
+        self._shared = []
+        if self._flags is not None:
+            self._flags.free()
+            self._flags = None
 
     def launches_per_propagation(self, K):
-        per_step = 1 if self.plan.world > 1 else 0  # pack
+        per_step = (2 if self.push else 1) if self.plan.world > 1 else 0  # push (+ flag wait) / pack
         for st in (self.owned, self.halo_part):
             if st.n > 0 and st.nnz > 0 or st is self.owned:
                 per_step += 2 if st.n_long > 0 else 1
         return K * per_step * len(self.parts)
 
-    # -- one half: exchange and compute -----------------------------------------------------
-    def _start_exchange(self, part, src):
-        """Pack + all-to-all of this part's halo rows on the comm stream, ordered after everything
-        already enqueued on the compute stream (the step that produced ``src``)."""
+    # -- phases of one step -------------------------------------------------------------------
+    def _push(self, part, src, delta):
+        """Fused pack + send + completion signal (epoch = base + delta) on the current stream."""
+        nat, L, p = self.nat, self.nat.lib(), self.plan
+        pi = self.parts.index(part)
+        bi = 0 if src.data_ptr() == part["buf"][0].data_ptr() else 1
+        F = part["F"]
+        nat.check(L.gnntf_halo_push_signal_f32(nat.ptr(src), F, nat.ptr(p.send_idx), nat.ptr(self._send_off),
+                                               nat.ptr(self._peer_ptrs[pi][bi]), nat.ptr(self._peer_row0), p.world,
+                                               int(p.send_idx.numel()), self._rotate, F, F, nat.ptr(self._done),
+                                               nat.ptr(self._peer_data_flags), p.rank, nat.ptr(self._epoch), int(delta),
+                                               nat.stream_ptr()), "halo_push_signal")
+
+    def _wait(self, row, delta):
+        """Current stream waits until flags[row, q] >= base + delta for every peer q."""
+        nat, p = self.nat, self.plan
+        flags = self._flags.tensor[row]
+        nat.check(nat.lib().gnntf_flags_wait(nat.ptr(flags), p.world, p.rank, nat.ptr(self._epoch), int(delta),
+                                             nat.stream_ptr()), "flags_wait")
+
+    def _ack(self, delta):
+        nat, p = self.nat, self.plan
+        nat.check(nat.lib().gnntf_flags_signal(nat.ptr(self._peer_ack_flags), p.world, p.rank, nat.ptr(self._epoch), int(delta),
+                                               nat.stream_ptr()), "flags_signal")
+
+    def _start_exchange(self, part, src, delta=0, first=False):
+        """This part's halo exchange for the step that reads ``src``, on the comm stream, ordered after
+        everything already enqueued on the compute stream (the step that produced ``src``)."""
         nat, L, p = self.nat, self.nat.lib(), self.plan
         part["work"] = None
         if p.world == 1:
@@ -356,16 +435,10 @@ class ShardedPropagator:
         with torch.cuda.stream(self.comm_stream):
             self.comm_stream.wait_event(ready)
             if self.push:
-                # fused pack + send: rows go straight into the peers' halo regions of the SAME
-                # ping-pong buffer; a one-element all-reduce is the cross-rank completion barrier
-                pi = self.parts.index(part)
-                bi = 0 if src.data_ptr() == part["buf"][0].data_ptr() else 1
-                n_send = int(p.send_idx.numel())
-                if n_send > 0:
-                    nat.check(L.gnntf_halo_push_f32(nat.ptr(src), F, nat.ptr(p.send_idx), nat.ptr(self._send_off),
-                                                    nat.ptr(self._peer_ptrs[pi][bi]), nat.ptr(self._peer_row0), p.world,
-                                                    n_send, self._rotate, F, F, nat.stream_ptr()), "halo_push")
-                part["work"] = dist.all_reduce(self._flag, group=self.group, async_op=True)
+                if first:  # nobody may overwrite a halo buffer a peer is still reading from the previous propagation
+                    self._wait(1, 0)
+                self._push(part, src, delta)
+                part["work"] = ("flags", delta)
                 return
             send = self._send_buffer(part)
             if send.shape[0] > 0:
@@ -379,29 +452,62 @@ class ShardedPropagator:
             else:
                 part["work"] = exchange_halo(p, send, src[self.n_local:], self.group, async_op=True)
 
-    def _compute(self, part, src, dst, alpha):
+    def _pass1(self, part, src, dst, alpha):
+        """Every row over its owned columns; alpha=None: plain SpMM, else the full fused PPR epilogue."""
         nat, L = self.nat, self.nat.lib()
         F, st = part["F"], self.nat.stream_ptr()
-        # pass 1: every row over its owned columns, full epilogue (teleport term included)
         s1 = self.owned.struct(self.owned_val, F)
-        nat.check(L.gnntf_appnp_step_f32(ctypes.byref(s1), nat.ptr(src), nat.ptr(part["H0"]), nat.ptr(dst), F, F,
-                                         float(alpha), None, 1.0, nat.ACT_IDENTITY, st), "appnp_step")
-        if part["work"] is not None:
-            part["work"].wait()  # the compute stream waits for this part's halo rows
-            part["work"] = None
-        # pass 2: dst[boundary rows] += (1-a) * (entries over halo columns) . H_halo
+        if alpha is None:
+            nat.check(L.gnntf_spmm_f32(ctypes.byref(s1), nat.ptr(src), F, nat.ptr(dst), F, F, st), "spmm")
+        else:
+            nat.check(L.gnntf_appnp_step_f32(ctypes.byref(s1), nat.ptr(src), nat.ptr(part["H0"]), nat.ptr(dst), F, F,
+                                             float(alpha), None, 1.0, nat.ACT_IDENTITY, st), "appnp_step")
+
+    def _pass2(self, part, src, dst, alpha):
+        """dst[boundary rows] += (1-a) * (entries over halo columns) · H_halo."""
+        nat, L = self.nat, self.nat.lib()
         if self.halo_part.n > 0:
+            F = part["F"]
             s2 = self.halo_part.struct(self.halo_val, F)
-            nat.check(L.gnntf_spmm_acc_f32(ctypes.byref(s2), nat.ptr(src), F, nat.ptr(dst), F, F, 1.0 - float(alpha), st),
+            scale = 1.0 if alpha is None else 1.0 - float(alpha)
+            nat.check(L.gnntf_spmm_acc_f32(ctypes.byref(s2), nat.ptr(src), F, nat.ptr(dst), F, F, scale, nat.stream_ptr()),
                       "spmm_acc")
+
+    def _wait_exchange(self, part):
+        work = part["work"]
+        part["work"] = None
+        if work is None:
+            return
+        if isinstance(work, tuple):
+            self._wait(0, work[1])   # the compute stream spins on the peers' completion flags (device side)
+        else:
+            work.wait()              # NCCL work / emulation event
+
+    def _compute(self, part, src, dst, alpha):
+        self._pass1(part, src, dst, alpha)
+        self._wait_exchange(part)
+        self._pass2(part, src, dst, alpha)
 
     def _step(self, src, dst, alpha):
         """One un-pipelined step of the first part (kept for the single-process emulation test)."""
         self._start_exchange(self.parts[0], src)
         self._compute(self.parts[0], src, dst, alpha)
 
+    def _finish(self, K):
+        """End of a propagation in push mode: join the comm stream, tell the peers this rank is done with its
+        halo buffers, advance the epoch base (a device scalar: the sequence replays under a CUDA graph)."""
+        if not self.push:
+            return
+        if self.comm_stream is not None:
+            joined = torch.cuda.Event()
+            joined.record(self.comm_stream)
+            torch.cuda.current_stream().wait_event(joined)
+        self._ack(K)
+        self._epoch.add_(K)
+
     def propagate(self, H0_local, alpha=0.1, iterations=10):
-        """K fused steps on this shard; returns this rank's rows of H_K ([n_local, F])."""
+        """K fused steps on this shard; returns this rank's rows of H_K ([n_local, F]) — a VIEW of an internal
+        ping-pong buffer, valid until the next call (clone it to keep it)."""
         cur = []
         for part in self.parts:
             part["H0"].copy_(H0_local[:, part["col0"]:part["col0"] + part["F"]])
@@ -410,22 +516,36 @@ class ShardedPropagator:
             cur.append([src, dst])
         if iterations > 0:
             for part, (src, _) in zip(self.parts, cur):
-                self._start_exchange(part, src)
+                self._start_exchange(part, src, delta=1, first=True)
         for k in range(iterations):
             for part, pair in zip(self.parts, cur):
                 src, dst = pair
                 self._compute(part, src, dst, alpha)
                 pair[0], pair[1] = dst, src
                 if k + 1 < iterations:      # this half's next exchange overlaps the other half's compute
-                    self._start_exchange(part, pair[0])
+                    self._start_exchange(part, pair[0], delta=k + 2)
+        self._finish(iterations)
         if len(self.parts) == 1:
             return cur[0][0][:self.n_local]
         return torch.cat([pair[0][:self.n_local] for pair in cur], dim=1)
 
-    def propagate_host_timed(self, alpha, iterations, reps=3):
-        """End-to-end: pinned host H0 shard -> device, K steps, result shard -> host."""
+    def spmm(self, H_local):
+        """One sharded SpMM ``(Â·H)[lo:hi]`` (BASELINE config 5, the R-MAT sweep): a single halo exchange
+        overlapped with the owned-column pass."""
+        part = self.parts[0]
+        assert len(self.parts) == 1
+        src, dst = part["buf"]
+        src[:self.n_local].copy_(H_local)
+        self._start_exchange(part, src, delta=1, first=True)
+        self._compute(part, src, dst, None)
+        self._finish(1)
+        return dst[:self.n_local]
+
+    def propagate_host_timed(self, H0_host, alpha, iterations, reps=3):
+        """End-to-end: this shard's rows of H0 in pinned host memory -> device, K steps, result shard -> host.
+        Returns the timing and the host result of the last repetition (for the caller's parity check)."""
         import time
-        host_in = torch.randn((self.n_local, self.F), dtype=torch.float32).pin_memory()
+        host_in = H0_host if H0_host.is_pinned() else H0_host.pin_memory()
         host_out = torch.empty_like(host_in).pin_memory()
         dev_in = torch.empty((self.n_local, self.F), dtype=torch.float32, device=self.H0.device)
 
@@ -449,4 +569,48 @@ class ShardedPropagator:
         if multi:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             dist.all_reduce(nbytes, op=dist.ReduceOp.SUM)
-        return {"seconds": float(t.item()), "h2d": int(nbytes.item()), "d2h": int(nbytes.item())}
+        return {"seconds": float(t.item()), "h2d": int(nbytes.item()), "d2h": int(nbytes.item()), "host_out": host_out}
+
+
+# ----------------------------------------------------------------------------------------------
+# Single-process emulation of the ranks on ONE GPU (tests): same kernels, same tables, same flags
+# ----------------------------------------------------------------------------------------------
+def connect_local(props):
+    """Wire ``props[r]`` (ShardedPropagator(..., peers="local") of rank r, all in this process and on one
+    device) to each other: the peer tables point straight at the other objects' buffers."""
+    everyone = [pr._layout() for pr in props]
+    for pr in props:
+        pr._build_tables(everyone, lambda q, pi, bi: props[q]._shared[pi][bi].ptr, lambda q: props[q]._flags.ptr)
+
+
+def propagate_lockstep(props, H0_locals, alpha=0.1, iterations=10, spmm_only=False):
+    """The sequence :meth:`ShardedPropagator.propagate` enqueues per rank, interleaved over all emulated
+    ranks on ONE stream so that every flag is written before the kernel that waits for it starts
+    (kernels that wait on one another must never share a GPU concurrently).  Returns the per-rank results."""
+    cur = []
+    for pr, H0 in zip(props, H0_locals):
+        part = pr.parts[0]
+        part["H0"].copy_(H0)
+        src, dst = part["buf"]
+        src[:pr.n_local].copy_(H0)
+        cur.append([src, dst])
+    K = 1 if spmm_only else iterations
+    a = None if spmm_only else alpha
+    for pr, (src, _) in zip(props, cur):
+        pr._wait(1, 0)
+        pr._push(pr.parts[0], src, 1)
+    for k in range(K):
+        for pr, (src, dst) in zip(props, cur):
+            pr._pass1(pr.parts[0], src, dst, a)
+        for pr, pair in zip(props, cur):
+            src, dst = pair
+            pr._wait(0, k + 1)
+            pr._pass2(pr.parts[0], src, dst, a)
+            pair[0], pair[1] = dst, src
+        if k + 1 < K:
+            for pr, (src, _) in zip(props, cur):
+                pr._push(pr.parts[0], src, k + 2)
+    for pr in props:
+        pr._ack(K)
+        pr._epoch.add_(K)
+    return [pair[0][:pr.n_local] for pr, pair in zip(props, cur)]

@@ -248,6 +248,27 @@ int gnntf_halo_push_f32(const float* H, int64_t ld, const int32_t* send_idx, con
                         float* const* peer_base, const int64_t* peer_row0, int n_peers,
                         int64_t n_send, int64_t rotate, int64_t ldo, int64_t F, void* stream);
 
+/* The same push, followed by a COMPLETION SIGNAL over peer memory: after all of this rank's rows have
+ * been stored (fenced at system scope), the last CTA writes  *epoch_base + epoch_delta  with
+ * st.release.sys into slot `my_slot` of every peer's flag array (peer_flags: DEVICE array of n_peers
+ * pointers, NULL = skip; each flag array is int32 [n_ranks] in that peer's memory, mapped with CUDA
+ * IPC).  done_counter: one zeroed int32 in local memory (left at zero).  epoch_base is a DEVICE scalar
+ * so that the whole K-step sequence can be captured in a CUDA graph and replayed with new epochs.
+ * gnntf_flags_wait: enqueue a one-warp kernel that spins (ld.acquire.sys) until flags[i] >= *epoch_base +
+ * epoch_delta for every i != skip — placed on the consumer's stream in front of the kernel that reads
+ * the halo rows; traps after ~4 s if a peer never arrives.  gnntf_flags_signal: publish an epoch to the
+ * peers without pushing rows (end-of-propagation acknowledgement: "my halo buffers may be overwritten").
+ * Each rank must run on its own GPU: a spinning kernel and the kernel it waits for must be co-resident. */
+int gnntf_halo_push_signal_f32(const float* H, int64_t ld, const int32_t* send_idx, const int64_t* send_off,
+                               float* const* peer_base, const int64_t* peer_row0, int n_peers,
+                               int64_t n_send, int64_t rotate, int64_t ldo, int64_t F,
+                               int32_t* done_counter, int32_t* const* peer_flags, int my_slot,
+                               const int32_t* epoch_base, int32_t epoch_delta, void* stream);
+int gnntf_flags_wait(const int32_t* flags, int n, int skip, const int32_t* epoch_base, int32_t epoch_delta,
+                     void* stream);
+int gnntf_flags_signal(int32_t* const* peer_flags, int n_peers, int my_slot, const int32_t* epoch_base,
+                       int32_t epoch_delta, void* stream);
+
 /* Peer-memory plumbing for gnntf_halo_push_f32 (the only entry points that allocate; used once at
  * shard set-up).  gnntf_ipc_alloc: cudaMalloc + cudaIpcGetMemHandle (handle = 64 bytes, shipped to
  * the peers through the host's own channel, e.g. torch.distributed.all_gather_object).

@@ -530,6 +530,85 @@ def test_sharded_propagator_emulated_ranks(world):
     assert props[0].owned.nnz + props[0].halo_part.nnz == props[0].nnz_local and props[0].halo_part.nnz > 0
 
 
+def _emulated_plans(gdist, A, world):
+    csr = A.csr
+    bounds = gdist.partition_bounds(csr.row_ptr, world)
+    first = [gdist.build_shard_plan(csr.row_ptr, csr.col_idx, A.val, r, world, peer_wants=lambda d: torch.empty(0))
+             for r in range(world)]          # pass 1: learn every rank's halo
+    return [gdist.build_shard_plan(csr.row_ptr, csr.col_idx, A.val, r, world,
+                                   peer_wants=lambda d, r=r: gdist.wanted_rows(first[d].halo_cols, bounds, r))
+            for r in range(world)]
+
+
+@pytest.mark.parametrize("n_peers,F,rotate_frac", [(2, 100, 0.5), (3, 40, 0.3), (4, 48, 0.0), (5, 52, 0.9), (8, 100, 0.37),
+                                                   (4, 7, 0.5), (3, 47, 0.2)])
+def test_halo_push_kernel_on_one_gpu(n_peers, F, rotate_frac):
+    """gnntf_halo_push_f32 with the peer pointers aimed at buffers on THIS device: every destination
+    receives exactly its slice of the send list (float4 path for F % 4 == 0, scalar otherwise), for
+    any rotation of the starting row, and nothing outside its halo region is touched."""
+    gnntf = _gnntf()
+    nat, L = gnntf._native, gnntf._native.lib()
+    rng = np.random.default_rng(n_peers * 100 + F)
+    n_src = 5000
+    H = torch.from_numpy(rng.standard_normal((n_src, F)).astype(np.float32)).cuda()
+    counts = [0] + [int(x) for x in rng.integers(0, 3000, n_peers - 1)]            # slot 0 plays "myself": nothing sent
+    if n_peers > 2:
+        counts[2] = 0                                                               # a peer that needs nothing (NULL pointer)
+    send_idx = torch.from_numpy(rng.integers(0, n_src, sum(counts)).astype(np.int32)).cuda()
+    off = np.concatenate([[0], np.cumsum(counts)]).astype(np.int64)
+    row0 = rng.integers(0, 50, n_peers).astype(np.int64)
+    bufs = [torch.full((int(row0[d]) + counts[d] + 7, F), -7.0, device="cuda") for d in range(n_peers)]
+    ptrs = torch.tensor([0 if counts[d] == 0 else bufs[d].data_ptr() for d in range(n_peers)], dtype=torch.int64, device="cuda")
+    n_send = int(off[-1])
+    rotate = int(rotate_frac * n_send) if n_send else 0
+    off_d, row0_d = torch.from_numpy(off).cuda(), torch.from_numpy(row0).cuda()     # (kept alive across the launch)
+    nat.check(L.gnntf_halo_push_f32(nat.ptr(H), F, nat.ptr(send_idx), nat.ptr(off_d), nat.ptr(ptrs), nat.ptr(row0_d),
+                                    n_peers, n_send, rotate, F, F, nat.stream_ptr()))
+    torch.cuda.synchronize()
+    for d in range(n_peers):
+        lo, hi = int(off[d]), int(off[d + 1])
+        r0 = int(row0[d])
+        assert torch.equal(bufs[d][r0:r0 + counts[d]], H[send_idx[lo:hi].long()])
+        assert torch.all(bufs[d][:r0] == -7.0) and torch.all(bufs[d][r0 + counts[d]:] == -7.0)
+
+
+@pytest.mark.parametrize("world,F,K", [(2, 40, 10), (2, 100, 1), (3, 52, 3), (4, 48, 10), (8, 100, 3), (4, 7, 2)])
+def test_sharded_push_loop_with_emulated_peers(world, F, K):
+    """The full ShardedPropagator(push=True) loop — fused pack+send+signal kernel, epoch flags in (peer)
+    memory, flag-wait kernels, two-pass step — with every rank emulated in this process on one GPU and
+    the peer tables aimed at the other ranks' buffers.  Several propagations back to back (odd K too:
+    the buffer-reuse hazard ADVICE r1 describes), then a sharded plain SpMM."""
+    gnntf = _gnntf()
+    from gnntf import dist as gdist
+    n, edges = synthetic.shaped_edges("arxiv", seed=0, device="cuda", scale=0.15)
+    adj = gnntf.edges2adj(edges, None, n)
+    A = adj.normalized("symmetric")
+    plans = _emulated_plans(gdist, A, world)
+    assert sum(p.n_local for p in plans) == n and any(p.n_halo > 0 for p in plans)
+    props = [gdist.ShardedPropagator(adj, A, F, r, world, plan=plans[r], push=True, peers="local") for r in range(world)]
+    assert all(p.push for p in props)
+    gdist.connect_local(props)
+    for call in range(3):
+        H0 = synthetic.features(n, F, 10 + call, "cuda")
+        expect = gnntf.appnp_propagate(A, H0, 0.1, K)
+        outs = gdist.propagate_lockstep(props, [H0[p.lo:p.hi] for p in props], 0.1, K)
+        got = torch.cat(outs)
+        oracle.assert_close(_np(got), _np(expect), what=f"push loop world={world} F={F} K={K} call {call}",
+                            floor=oracle.FLOOR_REORDERED)
+    assert all(int(p._epoch.item()) == 3 * K for p in props)                 # epochs advanced once per step
+    flags = torch.stack([p._flags.tensor for p in props]).cpu()             # [rank, 2, source]
+    for r in range(world):
+        for q in range(world):
+            if q != r:
+                assert int(flags[r, 0, q]) == 3 * K and int(flags[r, 1, q]) == 3 * K, (r, q, flags[r])
+    H = synthetic.features(n, F, 99, "cuda")
+    outs = gdist.propagate_lockstep(props, [H[p.lo:p.hi] for p in props], spmm_only=True)
+    oracle.assert_close(_np(torch.cat(outs)), _np(gnntf.sparse_dense_matmul(A, H)), what=f"sharded SpMM world={world} F={F}",
+                        floor=oracle.FLOOR_REORDERED)
+    for p in props:
+        p.close()
+
+
 def test_sharded_propagator_column_halves_world1_matches():
     """The two-half software pipeline (used when world > 1) on one rank: same result as one chain."""
     gnntf = _gnntf()
