@@ -293,6 +293,7 @@ def gpu_arm(args):
         c0, c1 = gdist.column_range(F_run, C, grid.c)
         prop = gdist.ShardedPropagator(adj, A, c1 - c0, grid.r, R, group=grid.row_group, halves=args.halves or None,
                                        push=not args.nccl_exchange)
+        prop.use_graph = not args.no_graph
         log(f"[rank {rank} = row group {grid.r}/{R}, column group {grid.c}/{C}] rows {prop.lo}:{prop.hi} cols {c0}:{c1} "
             f"nnz {prop.nnz_local} halo rows {prop.n_halo} owned-column entries {prop.owned.nnz} "
             f"halo-column entries {prop.halo_part.nnz} (rows {prop.halo_part.n})")
@@ -369,6 +370,8 @@ def gpu_arm(args):
             "csr_build_ms": build_s * 1e3,
         }
         if world > 1:
+            result["config"]["k_step_launch"] = ("one CUDA graph replay per propagation (both streams captured)"
+                                                 if any(isinstance(v, tuple) for v in prop._graphs.values()) else "launched step by step from the host")
             result["roofline"]["note"] += f"; aggregate over {world} GPUs, peak is per-GPU x {world}"
             result["roofline"]["peak"] = hbm_peak * world
             result["roofline"]["frac"] = achieved / (hbm_peak * world)
@@ -487,6 +490,7 @@ def main():
     ap.add_argument("--grid", default="", help="multi-GPU layout ROWSxCOLS (default: gnntf.dist.choose_grid)")
     ap.add_argument("--nccl-exchange", action="store_true", help="multi-GPU: halo rows by NCCL all-to-all instead of the fused peer-memory push")
     ap.add_argument("--halves", type=int, default=0, help="multi-GPU: feature-column chains to pipeline (0 = default)")
+    ap.add_argument("--no-graph", action="store_true", help="multi-GPU: launch every step from the host instead of replaying a CUDA graph")
     args = ap.parse_args()
     if args.impl == "reference":
         reference_arm(args)

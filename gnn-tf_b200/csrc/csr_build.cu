@@ -224,7 +224,7 @@ __global__ void scale_values_kernel(const int32_t* __restrict__ row_ptr, const i
                     vT = mT;
                 }
             }
-            norm_val[p] = v;
+            if (norm_val) norm_val[p] = v;
             if (norm_val_T) norm_val_T[p] = vT;
             if (norm_val_coo) norm_val_coo[q] = v;
         }
@@ -338,8 +338,8 @@ extern "C" int gnntf_normalize_f32(const int32_t* row_ptr, const int32_t* col_id
     if ((eye_mode == GNNTF_EYE_NONE) != (nnz == n_graph) && n > 0) return GNNTF_E_SIZE;
     if (n == 0) return GNNTF_OK;
     if (row_ptr == nullptr || deg == nullptr || dinv == nullptr) return GNNTF_E_NULL;
-    if (nnz > 0 && (col_idx == nullptr || raw_val == nullptr || coo_pos == nullptr || norm_val == nullptr))
-        return GNNTF_E_NULL;
+    if (nnz > 0 && (col_idx == nullptr || raw_val == nullptr || coo_pos == nullptr)) return GNNTF_E_NULL;
+    if (nnz > 0 && norm_val == nullptr && norm_val_T == nullptr && norm_val_coo == nullptr) return GNNTF_E_NULL;  // nothing to produce
     if (directed && norm_val_T != nullptr) return GNNTF_E_MODE;
     cudaStream_t st = (cudaStream_t)stream;
     const int threads = 256;

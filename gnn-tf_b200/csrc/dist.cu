@@ -7,7 +7,8 @@
 #include <cstdlib>
 #include <cstring>
 
-#include "common.cuh"
+#include "push.cuh"
+#include "spmm.cuh"
 
 namespace gnntf {
 
@@ -29,88 +30,14 @@ __global__ void halo_pack_kernel(const float* __restrict__ H, int64_t ld, const 
 // row (G sized to the row width), a warp runs 32/G rows side by side and every group keeps U rows
 // in flight (index loads, then all row loads, then all remote stores): the first version — one warp
 // per row, one row at a time — was latency-bound at 233 GB/s (profiles/r1, N=8 phase timing).
-__device__ __forceinline__ void st_release_sys(int32_t* p, int32_t v) {
-    asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-__device__ __forceinline__ int32_t ld_acquire_sys(const int32_t* p) {
-    int32_t v;
-    asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
-
-// Completion signal of a push (all arguments NULL/0 = no signalling).  Every CTA fences its remote
-// stores at system scope and counts itself in; the LAST one publishes `*epoch_base + epoch_delta` into
-// slot `my_slot` of every destination's flag array with a release store over NVLink, so a consumer
-// that acquires the flag also sees every row this rank pushed (and the counter is left at zero for
-// the next launch).  This replaces the host-issued NCCL all-reduce round 1 used as the barrier.
-struct PushSignal {
-    int32_t* done_counter;              // local, zero between launches
-    int32_t* const* peer_flags;         // [n_peers] flag arrays of the peers (peer memory), NULL entries skipped
-    const int32_t* epoch_base;          // device scalar advanced by the host side once per propagation
-    int32_t epoch_delta;
-    int32_t my_slot;
-};
-
-__device__ __forceinline__ void push_signal_tail(const PushSignal& sg, int n_peers) {
-    if (sg.done_counter == nullptr) return;
-    __threadfence_system();             // this thread's remote stores are performed before its CTA is counted
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        const int prev = atomicAdd(sg.done_counter, 1);
-        if (prev == (int)gridDim.x - 1) {
-            __threadfence_system();     // order the other CTAs' (fenced, counted) stores before the flags
-            const int32_t epoch = *sg.epoch_base + sg.epoch_delta;
-            for (int d = 0; d < n_peers; ++d)
-                if (sg.peer_flags[d] != nullptr) st_release_sys(sg.peer_flags[d] + sg.my_slot, epoch);
-            *sg.done_counter = 0;
-        }
-    }
-}
-
 template <int VEC, int G, int U>
 __global__ void halo_push_kernel(const float* __restrict__ H, int64_t ld, const int32_t* __restrict__ send_idx,
                                  const int64_t* __restrict__ send_off, float* const* __restrict__ peer_base,
                                  const int64_t* __restrict__ peer_row0, int n_peers, int64_t n_send,
                                  int64_t rotate, int64_t ldo, int F, PushSignal sg) {
-    constexpr int RPW = 32 / G;
-    const int lane = threadIdx.x & 31;
-    const int gl = lane % G;
-    const int64_t group = (((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5) * RPW + lane / G;
-    const int64_t n_groups = (((int64_t)gridDim.x * blockDim.x) >> 5) * RPW;
-    for (int64_t k0 = group; k0 < n_send; k0 += n_groups * U) {
-        const float* src[U];
-        float* dst[U];
-        bool ok[U];
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const int64_t k = k0 + (int64_t)u * n_groups;
-            ok[u] = k < n_send;
-            // every rank starts with a different destination, so at any moment each receiver is
-            // the target of (about) one sender instead of all of them
-            int64_t i = ok[u] ? k + rotate : 0;
-            if (i >= n_send) i -= n_send;
-            int d = 0;
-            while (d + 1 < n_peers && i >= send_off[d + 1]) ++d;   // n_peers <= 8: linear scan
-            src[u] = H + (int64_t)__ldg(send_idx + i) * ld;
-            dst[u] = ok[u] ? peer_base[d] + (peer_row0[d] + (i - send_off[d])) * ldo : nullptr;
-        }
-        if (F <= G * VEC) {  // one slot per lane: all U loads first, then all U stores
-            Vec<VEC> x[U];
-            const bool mine = gl * VEC < F;
-#pragma unroll
-            for (int u = 0; u < U; ++u)
-                if (ok[u] && mine) x[u] = Vec<VEC>::gather(src[u] + gl * VEC);
-#pragma unroll
-            for (int u = 0; u < U; ++u)
-                if (ok[u] && mine) x[u].store(dst[u] + gl * VEC);
-        } else {
-#pragma unroll
-            for (int u = 0; u < U; ++u)
-                if (ok[u])
-                    for (int f = gl * VEC; f < F; f += G * VEC) Vec<VEC>::gather(src[u] + f).store(dst[u] + f);
-        }
-    }
-    push_signal_tail(sg, n_peers);
+    halo_push_body<VEC, G, U>(H, ld, send_idx, send_off, peer_base, peer_row0, n_peers, n_send, rotate, ldo, F,
+                              (int)blockIdx.x, (int)gridDim.x);
+    push_signal_tail(sg, n_peers, (int)gridDim.x);
 }
 
 // Spin (one warp) until flags[i] >= *epoch_base + epoch_delta for every i != skip.  Enqueued on the
@@ -206,6 +133,47 @@ extern "C" int gnntf_halo_push_signal_f32(const float* H, int64_t ld, const int3
     if (my_slot < 0) return GNNTF_E_SIZE;
     return halo_push_impl(H, ld, send_idx, send_off, peer_base, peer_row0, n_peers, n_send, rotate, ldo, F,
                           PushSignal{done_counter, peer_flags, epoch_base, epoch_delta, my_slot}, (cudaStream_t)stream);
+}
+
+// One sharded step over the OWNED columns with the halo push of its input riding in the same launch.
+extern "C" int gnntf_step_push_f32(const gnntf_csr_t* A, const float* H_in, const float* H0, float* H_out, int64_t ld,
+                                   int64_t F, double alpha, const int32_t* send_idx, const int64_t* send_off,
+                                   float* const* peer_base, const int64_t* peer_row0, int n_peers, int64_t n_send,
+                                   int64_t rotate, int32_t* done_counter, int32_t* const* peer_flags, int my_slot,
+                                   const int32_t* epoch_base, int32_t epoch_delta, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (A == nullptr || done_counter == nullptr || peer_flags == nullptr || epoch_base == nullptr) return GNNTF_E_NULL;
+    if (F < 0 || F > 0x7fffffff || ld < F || n_send < 0 || n_peers < 1 || n_peers > 64 || my_slot < 0) return GNNTF_E_SIZE;
+    if (rotate < 0 || (n_send > 0 && rotate >= n_send)) return GNNTF_E_SIZE;
+    if (A->n_rows > 0 && F > 0 && (H_in == nullptr || H_out == nullptr)) return GNNTF_E_NULL;
+    if (n_send > 0 && (send_idx == nullptr || send_off == nullptr || peer_base == nullptr || peer_row0 == nullptr))
+        return GNNTF_E_NULL;
+    Epilogue e{};
+    e.s = (H0 != nullptr) ? (float)(1.0 - alpha) : 1.0f;   // H0 == NULL: plain SpMM (the R-MAT sweep)
+    e.H0 = H0;
+    e.ldh = ld;
+    e.t = (float)alpha;
+    e.act = GNNTF_ACT_IDENTITY;
+    e.C = H_out;
+    e.ldc = ld;
+    e.F = (int)F;
+    PushArgs pa{};
+    pa.n_ctas = (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div(n_send, 8), (int64_t)kNumSMs));
+    pa.send_idx = send_idx;
+    pa.send_off = send_off;
+    pa.peer_base = peer_base;
+    pa.peer_row0 = peer_row0;
+    pa.n_peers = n_peers;
+    pa.n_send = n_send;
+    pa.rotate = rotate;
+    pa.ldo = ld;
+    pa.sg = PushSignal{done_counter, peer_flags, epoch_base, epoch_delta, my_slot};
+    bool pushed = false;
+    int rc = spmm_dispatch(A, H_in, ld, e, st, &pa, &pushed);
+    if (rc != GNNTF_OK) return rc;
+    if (!pushed)  // scalar layout / empty shard: the push (or at least its signal) goes out as its own launch
+        rc = halo_push_impl(H_in, ld, send_idx, send_off, peer_base, peer_row0, n_peers, n_send, rotate, ld, F, pa.sg, st);
+    return rc;
 }
 
 extern "C" int gnntf_flags_wait(const int32_t* flags, int n, int skip, const int32_t* epoch_base, int32_t epoch_delta,

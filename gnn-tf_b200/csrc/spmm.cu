@@ -24,6 +24,7 @@
 
 #include <cooperative_groups.h>
 
+#include "push.cuh"
 #include "spmm.cuh"
 
 namespace gnntf {
@@ -574,14 +575,27 @@ __device__ __forceinline__ void rows4_body(const int* __restrict__ row_ptr, cons
 }
 
 
+// Grid layout along x: [ push CTAs | piece CTAs | row CTAs ].  The push CTAs (sharded runs only) send the
+// rows of the dense operand B that the peers need straight into their halo buffers over NVLink and
+// signal completion (push.cuh) while the rest of the grid computes: being the lowest block indices
+// they are dispatched first, so the exchange overlaps the whole launch without a second stream.
 template <int GROUP, int UNROLL, int THREADS, int MINB>
 __global__ void __launch_bounds__(THREADS, MINB)
 spmm_rows4_kernel(const int* __restrict__ row_ptr, const int* __restrict__ col_idx,
                   const float* __restrict__ val, const int* __restrict__ row_map,
                   const float* __restrict__ B, int64_t ldb, int n_rows, int long_threshold,
-                  int rounds, int piece_ctas, PieceArgs pieces, Epilogue epi) {
-    if ((int)blockIdx.x < piece_ctas) {  // CTA-uniform: this CTA works on pieces of split rows
-        const int piece = blockIdx.x * (THREADS / 32) + (threadIdx.x >> 5);
+                  int rounds, int piece_ctas, PieceArgs pieces, Epilogue epi, PushArgs push) {
+    if ((int)blockIdx.x < push.n_ctas) {  // CTA-uniform
+        if (blockIdx.y == 0) {
+            halo_push_body<4, GROUP, 4>(B, ldb, push.send_idx, push.send_off, push.peer_base, push.peer_row0, push.n_peers,
+                                        push.n_send, push.rotate, push.ldo, epi.F, (int)blockIdx.x, push.n_ctas);
+            push_signal_tail(push.sg, push.n_peers, push.n_ctas);
+        }
+        return;
+    }
+    const int bx = (int)blockIdx.x - push.n_ctas;
+    if (bx < piece_ctas) {  // CTA-uniform: this CTA works on pieces of split rows
+        const int piece = bx * (THREADS / 32) + (threadIdx.x >> 5);
         if (piece < pieces.n_chunks)
             process_piece<4, 1, GROUP, 4>(row_ptr, col_idx, val, B, ldb, pieces.chunk_row, pieces.chunk_begin, piece,
                                           pieces.chunk, pieces.partials, pieces.ldp, epi.F, blockIdx.y * (GROUP * 4));
@@ -589,7 +603,7 @@ spmm_rows4_kernel(const int* __restrict__ row_ptr, const int* __restrict__ col_i
     }
     __shared__ __align__(16) int2 cv_smem[THREADS / 32][2][32];
     rows4_body<GROUP, UNROLL, THREADS / 32, false>(row_ptr, col_idx, val, row_map, B, ldb, n_rows, long_threshold, rounds,
-                                                  (int64_t)blockIdx.x - piece_ctas, blockIdx.y * (GROUP * 4), epi, cv_smem);
+                                                  (int64_t)bx - piece_ctas, blockIdx.y * (GROUP * 4), epi, cv_smem);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -717,15 +731,16 @@ static int launch_cfg(const gnntf_csr_t* A, const float* B, int64_t ldb, const E
 
 // float4 fast path: spmm_rows4_kernel
 template <int GROUP, int THREADS, int MINB>
-static int launch_rows4_t(const gnntf_csr_t* A, const float* B, int64_t ldb, const Epilogue& epi, cudaStream_t st) {
+static int launch_rows4_t(const gnntf_csr_t* A, const float* B, int64_t ldb, const Epilogue& epi, cudaStream_t st,
+                          const PushArgs& push) {
     constexpr int UNROLL = (GROUP >= 8) ? 8 : 4;
     constexpr int NG = 32 / GROUP;
     constexpr int ROWS_PER_ROUND = (THREADS / 32) * NG;
     const int F = epi.F;
     const unsigned gy = (unsigned)ceil_div(F, GROUP * 4);
     const int thr = (A->n_long > 0) ? A->long_threshold : 0;
-    if (A->n_rows == 0) return GNNTF_OK;
-    const int rounds = pick_rounds(A->n_rows, ROWS_PER_ROUND, NG, MINB);
+    if (A->n_rows == 0 && push.n_ctas == 0) return GNNTF_OK;
+    const int rounds = pick_rounds(std::max<int64_t>(A->n_rows, 1), ROWS_PER_ROUND, NG, MINB);
     PieceArgs pieces{};
     int piece_ctas = 0;
     const int ldp = (int)round_up(F, 4);
@@ -733,9 +748,9 @@ static int launch_rows4_t(const gnntf_csr_t* A, const float* B, int64_t ldb, con
         pieces = PieceArgs{A->chunk_row, A->chunk_begin, A->n_chunks, A->chunk, A->partials, ldp};
         piece_ctas = (int)ceil_div(A->n_chunks, THREADS / 32);
     }
-    dim3 grid((unsigned)(piece_ctas + ceil_div(A->n_rows, (int64_t)ROWS_PER_ROUND * rounds)), gy);
+    dim3 grid((unsigned)(push.n_ctas + piece_ctas + ceil_div(A->n_rows, (int64_t)ROWS_PER_ROUND * rounds)), gy);
     spmm_rows4_kernel<GROUP, UNROLL, THREADS, MINB><<<grid, THREADS, 0, st>>>(
-        A->row_ptr, A->col_idx, A->val, A->row_map, B, ldb, (int)A->n_rows, thr, rounds, piece_ctas, pieces, epi);
+        A->row_ptr, A->col_idx, A->val, A->row_map, B, ldb, (int)A->n_rows, thr, rounds, piece_ctas, pieces, epi, push);
     GNNTF_LAUNCH_CHECK();
     if (A->n_long > 0) {
         spmm_long_reduce_kernel<<<A->n_long, 128, 0, st>>>(A->long_row, A->long_first_chunk, A->long_n_chunks,
@@ -746,10 +761,11 @@ static int launch_rows4_t(const gnntf_csr_t* A, const float* B, int64_t ldb, con
 }
 
 template <int GROUP>
-static int launch_rows4(const gnntf_csr_t* A, const float* B, int64_t ldb, const Epilogue& epi, cudaStream_t st) {
+static int launch_rows4(const gnntf_csr_t* A, const float* B, int64_t ldb, const Epilogue& epi, cudaStream_t st,
+                        const PushArgs& push) {
     // 256 threads x 5 CTAs per SM (48 registers): A/B against 256x4, 256x3, 192x6, 128x8 — all within 2 %
     // on the arxiv and products shapes (profiles/r2/06)
-    return launch_rows4_t<GROUP, 256, 5>(A, B, ldb, epi, st);
+    return launch_rows4_t<GROUP, 256, 5>(A, B, ldb, epi, st, push);
 }
 
 
@@ -829,7 +845,9 @@ int validate_csr(const gnntf_csr_t* A) {
 
 // C (and ACC) = epilogue(A·B).  Chooses the lane mapping from F and the alignment of every
 // operand; see the file header.
-int spmm_dispatch(const gnntf_csr_t* A, const float* B, int64_t ldb, Epilogue epi, cudaStream_t st) {
+int spmm_dispatch(const gnntf_csr_t* A, const float* B, int64_t ldb, Epilogue epi, cudaStream_t st,
+                  const PushArgs* push, bool* push_done) {
+    if (push_done) *push_done = false;
     int rc = validate_csr(A);
     if (rc != GNNTF_OK) return rc;
     const int64_t F = epi.F;
@@ -849,12 +867,17 @@ int spmm_dispatch(const gnntf_csr_t* A, const float* B, int64_t ldb, Epilogue ep
     if (epi.keep) v4 = false;  // byte mask rows are F-strided: keep the scalar path
 
     if (v4) {
+        PushArgs pa{};
+        if (push != nullptr && push->n_ctas > 0 && push->ldo % 4 == 0) {  // the push rides in this launch
+            pa = *push;
+            if (push_done) *push_done = true;
+        }
         const int64_t slots = F / 4;
-        if (slots <= 4) return launch_rows4<4>(A, B, ldb, epi, st);
-        if (slots <= 8) return launch_rows4<8>(A, B, ldb, epi, st);
-        if (slots <= 16) return launch_rows4<16>(A, B, ldb, epi, st);
+        if (slots <= 4) return launch_rows4<4>(A, B, ldb, epi, st, pa);
+        if (slots <= 8) return launch_rows4<8>(A, B, ldb, epi, st, pa);
+        if (slots <= 16) return launch_rows4<16>(A, B, ldb, epi, st, pa);
         // wider rows: 128-float tiles over grid.y (multi-slot mappings spilled and lost, profiles/r1/09)
-        return launch_rows4<32>(A, B, ldb, epi, st);
+        return launch_rows4<32>(A, B, ldb, epi, st, pa);
     }
     if (F <= 4) return launch_cfg<1, 1, 4>(A, B, ldb, epi, st);
     if (F <= 8) return launch_cfg<1, 1, 8>(A, B, ldb, epi, st);

@@ -1,6 +1,7 @@
 // Epilogue descriptor shared by the SpMM kernels and the APPNP drivers.
 #pragma once
 #include "common.cuh"
+#include "push.cuh"
 
 namespace gnntf {
 
@@ -23,7 +24,10 @@ struct Epilogue {
     int F;
 };
 
-int spmm_dispatch(const gnntf_csr_t* A, const float* B, int64_t ldb, Epilogue epi, cudaStream_t st);
+// `push` (sharded runs): the launch's leading CTAs also send rows of B to the peers; *push_done tells
+// the caller whether that happened (only the float4 path can host it; else the caller pushes separately).
+int spmm_dispatch(const gnntf_csr_t* A, const float* B, int64_t ldb, Epilogue epi, cudaStream_t st,
+                  const PushArgs* push = nullptr, bool* push_done = nullptr);
 int validate_csr(const gnntf_csr_t* A);
 // K fused APPNP steps in ONE cooperative launch when the whole step is a single wave of CTAs and no
 // row is split; *taken says whether it was enqueued (otherwise the caller launches step by step).

@@ -7,10 +7,11 @@ and per propagation step an exchange of exactly the halo feature rows each rank 
 overlapped with the SpMM of the rows that need no halo.
 
   rank r owns rows [lo_r, hi_r);  its CSR addresses  H_ext = [ owned rows | halo rows ]
-  step:  pack rows peers need (native kernel)  ->  all-to-all (NCCL over NVLink)      [comm]
-         fused APPNP step of ALL rows over their OWNED columns (the bulk of the entries;
-         needs no halo)                                                               [compute, overlaps]
-         wait for the halo  ->  accumulate the HALO-column entries of the boundary rows
+  step:  ONE launch: the leading CTAs send the rows the peers need straight into their halo buffers over
+         NVLink peer memory and publish an epoch flag (st.release.sys); the rest of the grid runs the
+         fused APPNP step of ALL rows over their OWNED columns (the bulk of the entries; needs no halo)
+         flag wait (ld.acquire.sys, one warp)  ->  accumulate the HALO-column entries of the boundary rows
+         (NCCL fallback: pack kernel + all-to-all on a second stream)
 (the shard's CSR is split by column, not by row: on power-law graphs almost every row touches
 some remote column, so a row split leaves nothing to overlap with — measured 6 % interior rows
 on the products shape at 2 GPUs).
@@ -255,7 +256,7 @@ class ShardedPropagator:
         from . import _native as nat
         from .sparse import CsrStructure
         self.nat = nat
-        self.group, self.F = group, int(F)
+        self.group, self.F, self.peers_mode = group, int(F), peers
         self._exchange = exchange  # test hook: single-process emulation of the all-to-all
         self.comm_stream = torch.cuda.Stream(priority=-1) if (world > 1 and torch.cuda.is_available() and peers == "ipc") else None
         csr = A.csr
@@ -277,6 +278,7 @@ class ShardedPropagator:
         self.push = bool(push) and p.world > 1 and exchange is None
         self.parts, col0, self._shared = [], 0, []
         self._opened, self._flags, self._closed = [], None, False
+        self.use_graph, self._graphs, self._graph_error = True, {}, None
         for w in widths:
             if self.push:
                 mats = [_SharedBuffer((n_ext, w), torch.float32, dev) for _ in range(2)]
@@ -368,6 +370,7 @@ class ShardedPropagator:
         if self._closed:
             return
         self._closed = True
+        self._graphs = {}
         if torch.cuda.is_available():
             torch.cuda.synchronize()
         multi = self.group is not None or (dist.is_available() and dist.is_initialized() and self.plan.world > 1
@@ -391,7 +394,7 @@ class ShardedPropagator:
             self._flags = None
 
     def launches_per_propagation(self, K):
-        per_step = (2 if self.push else 1) if self.plan.world > 1 else 0  # push (+ flag wait) / pack
+        per_step = 1 if self.plan.world > 1 else 0  # flag-wait kernel (the push rides in the pass-1 launch) / pack kernel
         for st in (self.owned, self.halo_part):
             if st.n > 0 and st.nnz > 0 or st is self.owned:
                 per_step += 2 if st.n_long > 0 else 1
@@ -409,6 +412,21 @@ class ShardedPropagator:
                                                int(p.send_idx.numel()), self._rotate, F, F, nat.ptr(self._done),
                                                nat.ptr(self._peer_data_flags), p.rank, nat.ptr(self._epoch), int(delta),
                                                nat.stream_ptr()), "halo_push_signal")
+
+    def _step_push(self, part, src, dst, alpha, delta):
+        """Pass 1 (every row over its owned columns) with the halo push of ``src`` and its completion signal
+        riding in the SAME launch (gnntf_step_push_f32): the leading CTAs of the grid send, the rest compute."""
+        nat, L, p = self.nat, self.nat.lib(), self.plan
+        pi = self.parts.index(part)
+        bi = 0 if src.data_ptr() == part["buf"][0].data_ptr() else 1
+        F = part["F"]
+        s1 = self.owned.struct(self.owned_val, F)
+        nat.check(L.gnntf_step_push_f32(ctypes.byref(s1), nat.ptr(src), nat.ptr(part["H0"]) if alpha is not None else None,
+                                        nat.ptr(dst), F, F, float(alpha if alpha is not None else 0.0), nat.ptr(p.send_idx),
+                                        nat.ptr(self._send_off), nat.ptr(self._peer_ptrs[pi][bi]), nat.ptr(self._peer_row0),
+                                        p.world, int(p.send_idx.numel()), self._rotate, nat.ptr(self._done),
+                                        nat.ptr(self._peer_data_flags), p.rank, nat.ptr(self._epoch), int(delta),
+                                        nat.stream_ptr()), "step_push")
 
     def _wait(self, row, delta):
         """Current stream waits until flags[row, q] >= base + delta for every peer q."""
@@ -434,12 +452,6 @@ class ShardedPropagator:
         ready.record()                                   # src complete on the compute stream
         with torch.cuda.stream(self.comm_stream):
             self.comm_stream.wait_event(ready)
-            if self.push:
-                if first:  # nobody may overwrite a halo buffer a peer is still reading from the previous propagation
-                    self._wait(1, 0)
-                self._push(part, src, delta)
-                part["work"] = ("flags", delta)
-                return
             send = self._send_buffer(part)
             if send.shape[0] > 0:
                 nat.check(L.gnntf_halo_pack_f32(nat.ptr(src), F, nat.ptr(p.send_idx), send.shape[0],
@@ -476,11 +488,7 @@ class ShardedPropagator:
     def _wait_exchange(self, part):
         work = part["work"]
         part["work"] = None
-        if work is None:
-            return
-        if isinstance(work, tuple):
-            self._wait(0, work[1])   # the compute stream spins on the peers' completion flags (device side)
-        else:
+        if work is not None:
             work.wait()              # NCCL work / emulation event
 
     def _compute(self, part, src, dst, alpha):
@@ -498,16 +506,49 @@ class ShardedPropagator:
         halo buffers, advance the epoch base (a device scalar: the sequence replays under a CUDA graph)."""
         if not self.push:
             return
-        if self.comm_stream is not None:
-            joined = torch.cuda.Event()
-            joined.record(self.comm_stream)
-            torch.cuda.current_stream().wait_event(joined)
         self._ack(K)
         self._epoch.add_(K)
 
     def propagate(self, H0_local, alpha=0.1, iterations=10):
         """K fused steps on this shard; returns this rank's rows of H_K ([n_local, F]) — a VIEW of an internal
-        ping-pong buffer, valid until the next call (clone it to keep it)."""
+        ping-pong buffer, valid until the next call (clone it to keep it).
+
+        In push mode the whole sequence (copies, pushes, flag waits, both passes of every step, on the two
+        streams) is captured into a CUDA graph on the second call with the same (alpha, K) and replayed
+        afterwards: no Python and no launch latency between the ~5 launches of a step.
+        The epochs the kernels signal and wait for live in a device scalar, so a replay uses fresh ones."""
+        key = (float(alpha), int(iterations))
+        if self.push and self.use_graph and self.peers_mode == "ipc" and iterations > 0:
+            entry = self._graphs.get(key)
+            if entry is None:                       # first call: eager (allocates workspaces), remember we saw it
+                self._graphs[key] = "warm"
+            elif entry == "warm":                   # second call: capture
+                try:
+                    self._graphs[key] = self._capture(key)
+                except Exception as err:            # keep working without the graph
+                    self._graphs[key] = "off"
+                    self._graph_error = err
+                    torch.cuda.synchronize()
+            entry = self._graphs[key]
+            if isinstance(entry, tuple):
+                graph, static_in, out = entry
+                static_in.copy_(H0_local)
+                graph.replay()
+                return out
+        return self._propagate_eager(H0_local, alpha, iterations)
+
+    def _capture(self, key):
+        alpha, iterations = key
+        static_in = torch.empty((self.n_local, self.F), dtype=torch.float32, device=self.H0.device)
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            out = self._propagate_eager(static_in, alpha, iterations)
+        return graph, static_in, out
+
+    def _propagate_eager(self, H0_local, alpha, iterations):
+        if self.push:
+            return self._propagate_push(H0_local, alpha, iterations)
         cur = []
         for part in self.parts:
             part["H0"].copy_(H0_local[:, part["col0"]:part["col0"] + part["F"]])
@@ -529,16 +570,46 @@ class ShardedPropagator:
             return cur[0][0][:self.n_local]
         return torch.cat([pair[0][:self.n_local] for pair in cur], dim=1)
 
+    def _propagate_push(self, H0_local, alpha, iterations, spmm_only=False):
+        """Push mode, ONE stream, per step:  [push of H_k ∥ owned-column pass] -> flag wait -> halo-column pass.
+        (alpha=None with spmm_only: a single sharded SpMM.)"""
+        cur = []
+        for part in self.parts:
+            if spmm_only:
+                src, dst = part["buf"]
+                src[:self.n_local].copy_(H0_local[:, part["col0"]:part["col0"] + part["F"]])
+            else:
+                part["H0"].copy_(H0_local[:, part["col0"]:part["col0"] + part["F"]])
+                src, dst = part["buf"]
+                src[:self.n_local].copy_(part["H0"])
+            cur.append([src, dst])
+        if iterations > 0:
+            self._wait(1, 0)      # every peer is done reading its halo buffers of the previous propagation
+        for k in range(iterations):
+            for part, pair in zip(self.parts, cur):
+                src, dst = pair
+                self._step_push(part, src, dst, alpha, k + 1)
+            for part, pair in zip(self.parts, cur):
+                src, dst = pair
+                self._wait(0, k + 1)
+                self._pass2(part, src, dst, alpha)
+                pair[0], pair[1] = dst, src
+        self._finish(iterations)
+        if len(self.parts) == 1:
+            return cur[0][0][:self.n_local]
+        return torch.cat([pair[0][:self.n_local] for pair in cur], dim=1)
+
     def spmm(self, H_local):
         """One sharded SpMM ``(Â·H)[lo:hi]`` (BASELINE config 5, the R-MAT sweep): a single halo exchange
         overlapped with the owned-column pass."""
         part = self.parts[0]
         assert len(self.parts) == 1
+        if self.push:
+            return self._propagate_push(H_local, None, 1, spmm_only=True)
         src, dst = part["buf"]
         src[:self.n_local].copy_(H_local)
         self._start_exchange(part, src, delta=1, first=True)
         self._compute(part, src, dst, None)
-        self._finish(1)
         return dst[:self.n_local]
 
     def propagate_host_timed(self, H0_host, alpha, iterations, reps=3):
@@ -590,26 +661,23 @@ def propagate_lockstep(props, H0_locals, alpha=0.1, iterations=10, spmm_only=Fal
     cur = []
     for pr, H0 in zip(props, H0_locals):
         part = pr.parts[0]
-        part["H0"].copy_(H0)
+        if not spmm_only:
+            part["H0"].copy_(H0)
         src, dst = part["buf"]
         src[:pr.n_local].copy_(H0)
         cur.append([src, dst])
     K = 1 if spmm_only else iterations
     a = None if spmm_only else alpha
-    for pr, (src, _) in zip(props, cur):
+    for pr in props:
         pr._wait(1, 0)
-        pr._push(pr.parts[0], src, 1)
     for k in range(K):
         for pr, (src, dst) in zip(props, cur):
-            pr._pass1(pr.parts[0], src, dst, a)
+            pr._step_push(pr.parts[0], src, dst, a, k + 1)      # push of H_k + owned-column pass, one launch
         for pr, pair in zip(props, cur):
             src, dst = pair
             pr._wait(0, k + 1)
             pr._pass2(pr.parts[0], src, dst, a)
             pair[0], pair[1] = dst, src
-        if k + 1 < K:
-            for pr, (src, _) in zip(props, cur):
-                pr._push(pr.parts[0], src, k + 2)
     for pr in props:
         pr._ack(K)
         pr._epoch.add_(K)

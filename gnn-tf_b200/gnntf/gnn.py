@@ -121,14 +121,17 @@ class PPRIteration(Layer):
         first = run[0]
         K = len(run)
         if architecture.is_training() and first.graph_dropout != 0:
-            adjs = [architecture.get_adjacency(first.graph_dropout) for _ in range(K)]  # one mask per iteration
-            for layer, G in zip(run, adjs):
-                layer.G = G
+            # one edge mask per iteration (filter.py:18); the adjacencies themselves are never materialised
+            drawn = [architecture.sparse_dropout(architecture.graph, first.graph_dropout) for _ in range(K)]
+            for layer, G in zip(run, drawn):
+                layer.G = G                      # the masked (un-normalised) adjacency of this iteration
+            out = ops.appnp_propagate_masked(architecture.graph, [G.keep for G in drawn], first.graph_dropout, features,
+                                             first.restart_probability)
         else:
             adjs = architecture.get_adjacency(first.graph_dropout)
             for layer in run:
                 layer.G = adjs
-        out = ops.appnp_propagate(adjs, features, first.restart_probability, K)
+            out = ops.appnp_propagate(adjs, features, first.restart_probability, K)
         for layer in run[:-1]:  # intermediate iterates are not materialised by the fused op:
             layer.value = None  # a stale value from an earlier un-fused call must not survive
         run[-1].value = out

@@ -210,6 +210,71 @@ def appnp_propagate(adjs, H0, alpha=0.1, iterations=10):
     return _Propagate.apply(adjs, _dense(H0), float(alpha), int(iterations))
 
 
+class _PropagateMasked(torch.autograd.Function):
+    """Training-mode K-step propagation (one edge keep-mask per iteration, filter.py:18 → layered.py:47-50)
+    WITHOUT K materialised adjacencies: each iteration normalises into one reused scratch value array,
+    runs its fused step, and only its mask (uint8 per COO entry) survives; the backward pass recomputes
+    the transposed values of iteration k from mask k into the same scratch.  products shape, K = 10:
+    1.9 GB of state instead of 11 GB (SURVEY §7 "recompute from the mask")."""
+
+    @staticmethod
+    def forward(ctx, base, masks, rate, H0, alpha):
+        L = nat.lib()
+        K = len(masks)
+        H0p, F = _pad4(H0.contiguous())
+        n, nnz, dev = base.n, base.csr.nnz, H0p.device
+        f32 = dict(dtype=torch.float32, device=dev)
+        deg, dinv, val = torch.empty(n, **f32), torch.empty(n, **f32), torch.empty(nnz, **f32)
+        bufs = [torch.empty_like(H0p), torch.empty_like(H0p)]
+        src = H0p
+        for k in range(K):
+            base.normalize_into(masks[k], rate, deg, dinv, val=val)
+            dst = bufs[k & 1]
+            st = base.csr.struct(val, H0p.shape[1])
+            nat.check(L.gnntf_appnp_step_f32(ctypes.byref(st), nat.ptr(src), nat.ptr(H0p), nat.ptr(dst), _ld(H0p), H0p.shape[1],
+                                             float(alpha), None, 1.0, nat.ACT_IDENTITY, nat.stream_ptr()), "appnp_step")
+            src = dst
+        ctx.base, ctx.masks, ctx.rate, ctx.alpha = base, masks, rate, alpha
+        out = src if K > 0 else H0p.clone()
+        return out if out.shape[1] == F else out[:, :F].contiguous()
+
+    @staticmethod
+    def backward(ctx, g):
+        L = nat.lib()
+        base, masks, K, a = ctx.base, ctx.masks, len(ctx.masks), float(ctx.alpha)
+        g, F_orig = _pad4(g.contiguous())
+        n, nnz, dev, F = base.n, base.csr.nnz, g.device, g.shape[1]
+        f32 = dict(dtype=torch.float32, device=dev)
+        deg, dinv, valT = torch.empty(n, **f32), torch.empty(n, **f32), torch.empty(nnz, **f32)
+        dH0 = g * a if K > 0 else g.clone()          # dH0 += a·g_K
+        cur = g
+        bufs = [torch.empty_like(g), torch.empty_like(g)]
+        for k in range(K - 1, -1, -1):               # g_k = (1-a)·Â_kᵀ·g_{k+1};  dH0 += a·g_k (k > 0) ... + g_0
+            base.normalize_into(masks[k], ctx.rate, deg, dinv, val=None, val_T=valT)
+            st = base.csr.struct(valT, F)
+            dst = bufs[k & 1]
+            nat.check(L.gnntf_spmm_f32(ctypes.byref(st), nat.ptr(cur), _ld(cur), nat.ptr(dst), _ld(dst), F, nat.stream_ptr()), "spmm")
+            dst.mul_(1.0 - a)
+            dH0.add_(dst, alpha=(a if k > 0 else 1.0))
+            cur = dst
+        return None, None, None, (dH0 if F == F_orig else dH0[:, :F_orig].contiguous()), None
+
+
+def appnp_propagate_masked(base, keep_masks, rate, H0, alpha=0.1):
+    """K = len(keep_masks) fused PPR iterations in TRAINING mode: iteration k uses the adjacency
+    ``get_adjacency`` builds from edge keep-mask k (COO order, one Bernoulli per entry).  Memory-light
+    form of ``appnp_propagate([adj.normalized(keep_mask=m, rate=rate) for m in keep_masks], ...)`` with
+    identical results; undirected adjacencies in their own node order only."""
+    if base.directed or base.perm is not None:
+        adjs = [base.normalized("symmetric", keep_mask=m, rate=rate) for m in keep_masks]
+        return appnp_propagate(adjs, H0, alpha, len(keep_masks))
+    masks = [m.to(device=base.raw_val.device, dtype=torch.uint8).contiguous() for m in keep_masks]
+    for m in masks:
+        if m.numel() != base.n_graph:
+            raise Exception(f"edge keep-mask must have one entry per COO entry ({base.n_graph}), got {m.numel()}")
+    return _PropagateMasked.apply(base, masks, float(rate), _dense(H0), float(alpha))
+
+
 def appnp_propagate_host(adj, H0_host, alpha=0.1, iterations=10, out_host=None, bufs=None):
     """End-to-end form with HOST feature buffers (pinned for full speed): H2D copy, K fused steps,
     D2H copy, all on the current stream; returns the host tensor after synchronising."""

@@ -116,7 +116,7 @@ int gnntf_csr_build(const int64_t* edges, const float* weights, int64_t n, int64
  * n eye entries (if the CSR was built with add_eye) take part (BEFORE: normalised like any
  * entry; AFTER: excluded from the degree, value stays 1).  directed != 0 means the COO list has
  * no appended reverse half, so column sums use float atomics instead of the partner trick.
- * Outputs: deg [n], dinv [n] (0 where deg == 0, divide_no_nan), norm_val [nnz] (CSR order),
+ * Outputs: deg [n], dinv [n] (0 where deg == 0, divide_no_nan), norm_val [nnz] (CSR order) or NULL,
  * norm_val_T [nnz] or NULL (values of the TRANSPOSED matrix laid on the same CSR structure —
  * valid for undirected graphs only; equals norm_val when no mask is given),
  * norm_val_coo [nnz] or NULL (COO order: the .values of the SparseTensor get_adjacency returns).
@@ -264,6 +264,16 @@ int gnntf_halo_push_signal_f32(const float* H, int64_t ld, const int32_t* send_i
                                int64_t n_send, int64_t rotate, int64_t ldo, int64_t F,
                                int32_t* done_counter, int32_t* const* peer_flags, int my_slot,
                                const int32_t* epoch_base, int32_t epoch_delta, void* stream);
+/* One step of a shard over its OWNED columns — H_out = (1-alpha)·A·H_in + alpha·H0, or plain A·H_in when
+ * H0 == NULL — with the halo push of H_in's rows (and its completion signal, as above) riding in the SAME
+ * launch: the leading CTAs of the SpMM grid do the push, so it is dispatched first and overlaps the
+ * whole pass without a second stream.  Peer halo buffers have leading dimension ld.  Layouts the float4
+ * path cannot take fall back to two launches on `stream` (same result). */
+int gnntf_step_push_f32(const gnntf_csr_t* A, const float* H_in, const float* H0, float* H_out, int64_t ld,
+                        int64_t F, double alpha, const int32_t* send_idx, const int64_t* send_off,
+                        float* const* peer_base, const int64_t* peer_row0, int n_peers, int64_t n_send,
+                        int64_t rotate, int32_t* done_counter, int32_t* const* peer_flags, int my_slot,
+                        const int32_t* epoch_base, int32_t epoch_delta, void* stream);
 int gnntf_flags_wait(const int32_t* flags, int n, int skip, const int32_t* epoch_base, int32_t epoch_delta,
                      void* stream);
 int gnntf_flags_signal(int32_t* const* peer_flags, int n_peers, int my_slot, const int32_t* epoch_base,

@@ -31,7 +31,7 @@ ok, worst = True, 0.0
 # repeated calls exercise buffer reuse across propagations; odd K with a DIFFERENT H0 per call is the
 # write-after-read hazard of the peer-memory push: a fast rank must not overwrite halo rows
 # a slow peer is still reading from the previous call
-for call, K in enumerate([10, 1, 3, 1, 10, 3]):
+for call, K in enumerate([10, 1, 3, 1, 10, 3, 10, 1, 3]):   # 2nd use of a K captures a CUDA graph, 3rd replays it
     H0 = synthetic.features(n, F, 1 + call, "cuda")
     expect = gnntf.appnp_propagate(A, H0, 0.1, K)
     if call % 2 == rank % 2:
@@ -49,7 +49,8 @@ err = (got - ref).abs().max().item() / ref.abs().max().item()
 worst = max(worst, err)
 ok = ok and err < 1e-5
 torch.cuda.synchronize()
-print(f"rank {rank} grid {R}x{C} push={prop.push} rows {prop.lo}:{prop.hi} cols {c0}:{c1} halo {prop.n_halo} max rel err {worst:.2e} {'PASS' if ok else 'FAIL'}", flush=True)
+graphs = sum(isinstance(v, tuple) for v in prop._graphs.values())
+print(f"rank {rank} grid {R}x{C} push={prop.push} graphs={graphs} rows {prop.lo}:{prop.hi} cols {c0}:{c1} halo {prop.n_halo} max rel err {worst:.2e} {'PASS' if ok else 'FAIL'}", flush=True)
 flag = torch.tensor([0.0 if ok else 1.0], device="cuda")
 dist.all_reduce(flag)
 prop.close()

@@ -203,3 +203,37 @@ def test_pubmed_gcn_training_forward_and_backward_vs_oracle():
     gb1 = gZ1.sum(0, keepdims=True)
     for name, w, ref in (("dW2", ws[3 - 1], gW2), ("db2", ws[3], gb2), ("dW1", ws[0], gW1), ("db1", ws[1], gb1)):
         oracle.assert_close(_np(w.var.grad), ref, what=f"PubMed GCN {name}", floor=0.05)
+
+
+# ------------------------------------------------------------------------------------------
+# Training-mode propagation at products scale: memory
+# ------------------------------------------------------------------------------------------
+def test_products_training_forward_backward_memory():
+    """APPNP's K = 10 training propagation at the products shape and class width (47 -> 48 columns):
+    one edge mask per iteration (filter.py:18), forward + backward, WITHOUT K materialised adjacencies.
+    Round 1 kept val + val_T per iteration (10 x 0.99 GB + masks); now only the masks survive."""
+    gnntf = _gnntf()
+    n, edges = synthetic.shaped_edges("products", seed=0, device="cuda")
+    adj = gnntf.edges2adj(edges, None, n)
+    del edges
+    torch.cuda.empty_cache()
+    torch.cuda.synchronize()
+    base = torch.cuda.memory_allocated()
+    torch.cuda.reset_peak_memory_stats()
+    F, K = 48, 10
+    g = torch.Generator(device="cuda").manual_seed(3)
+    masks = [torch.rand(adj.n_graph, device="cuda", generator=g) >= 0.5 for _ in range(K)]
+    H0 = synthetic.features(n, F, seed=1, device="cuda").requires_grad_(True)
+    out = gnntf.ops.appnp_propagate_masked(adj, masks, 0.5, H0, 0.1)
+    out.backward(torch.ones_like(out))
+    torch.cuda.synchronize()
+    peak_total = torch.cuda.max_memory_allocated() / 2**30
+    peak_extra = (torch.cuda.max_memory_allocated() - base) / 2**30
+    print(f"products training K=10 F={F}: adjacency {base / 2**30:.2f} GiB, peak total {peak_total:.2f} GiB, propagation {peak_extra:.2f} GiB")
+    assert peak_total < 12.0, (peak_total, peak_extra)
+    assert torch.isfinite(H0.grad).all()
+    # the backward of a linear map: <out, 1> differentiated w.r.t. H0 is the transposed operator applied to 1;
+    # check the adjoint identity <P(H0), G> = <H0, P^T(G)> with G = 1 on the full-size graph
+    lhs = out.double().sum().item()
+    rhs = (H0.detach().double() * H0.grad.double()).sum().item()
+    assert abs(lhs - rhs) <= 1e-5 * max(abs(lhs), 1.0), (lhs, rhs)

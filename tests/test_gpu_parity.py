@@ -955,3 +955,32 @@ def test_gcn_spectral_preserving_layer_and_structural_preprocessor():
         W, b = _np(layer.W), _np(layer.b)
         H = 2 * (oracle.relu(oracle.spmm_coo(idx, nv, H) @ W + b) - b)       # gcn.py:104-105, eval mode
     oracle.assert_close(out, H, what="GCN spectral-preserving + Structural", floor=oracle.FLOOR_REORDERED)
+
+
+# ------------------------------------------------------------------------------------------
+# Training mode without K materialised adjacencies
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("F,K", [(7, 3), (48, 10), (100, 2)])
+def test_masked_propagation_recomputed_from_masks_equals_materialised_adjacencies(F, K):
+    gnntf = _gnntf()
+    rng = np.random.default_rng(F + K)
+    n, e = 900, 9000
+    edges, w = _random_edges(n, e, seed=F)
+    adj = gnntf.edges2adj(edges, w, n)
+    masks = [torch.from_numpy(rng.random(adj.n_graph) >= 0.5).cuda() for _ in range(K)]
+    H0a = torch.from_numpy(rng.standard_normal((n, F)).astype(np.float32)).cuda().requires_grad_(True)
+    H0b = H0a.detach().clone().requires_grad_(True)
+    g = torch.from_numpy(rng.standard_normal((n, F)).astype(np.float32)).cuda()
+    out_a = gnntf.ops.appnp_propagate_masked(adj, masks, 0.5, H0a, 0.1)
+    out_b = gnntf.appnp_propagate([adj.normalized("symmetric", keep_mask=m, rate=0.5) for m in masks], H0b, 0.1, K)
+    assert torch.equal(out_a, out_b)                                     # same kernels on the same values
+    out_a.backward(g)
+    out_b.backward(g)
+    oracle.assert_close(_np(H0a.grad), _np(H0b.grad), what=f"masked backward F={F} K={K}", floor=oracle.FLOOR_REORDERED)
+    idx, val, _ = oracle.graph2adj_arrays(edges, w, n)
+    keeps = [_np(m) for m in masks]
+    expect = oracle.appnp_propagate(idx, val, n, _np(H0a.detach()), 0.1, K, 0.5, keeps, training=True)[-1]
+    oracle.assert_close(_np(out_a), expect, what=f"masked forward vs oracle F={F} K={K}")
+    nvs = [oracle.get_adjacency(idx, oracle.sparse_dropout(val, 0.5, k), n)[1] for k in keeps]
+    oracle.assert_close(_np(H0a.grad), oracle.appnp_propagate_bwd(idx, nvs, _np(g), 0.1), what="masked dH0 vs oracle",
+                        floor=oracle.FLOOR_REORDERED)
