@@ -7,8 +7,8 @@
 //
 //   GnntfSpmm             <- tf.sparse.sparse_dense_matmul(adj, H)        filter.py:19, gcn.py:88 ...
 //   GnntfAppnpPropagate   <- the K PPRIteration layers                    filter.py:17-22,34-35
-//   (graph2adj / get_adjacency run once per graph through the ctypes host shim or the two ops below)
-//   GnntfCsrBuild, GnntfNormalize
+//   (graph2adj / get_adjacency run once per graph through the ctypes host shim, gnntf_tf.py; this file
+//    registers no op for them)
 //
 // Kernels are stateless and re-entrant; every launch goes to the op's own GPU stream
 // (ctx->eigen_gpu_device().stream()), temporaries come from ctx->allocate_temp, so TF may call
