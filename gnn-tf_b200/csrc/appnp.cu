@@ -137,6 +137,20 @@ extern "C" int gnntf_appnp_propagate_bwd_f32(const gnntf_csr_t* AT_k, int K, con
     return GNNTF_OK;
 }
 
+// Host <-> device copies of a dense [n, F] host matrix and an [n, ld] device matrix.  Dense on both
+// sides: one linear DMA (2-D copies are issued row by row).
+static cudaError_t copy_in(float* dev, const float* host, int64_t n, int64_t ld, int64_t F, cudaStream_t st) {
+    if (ld == F) return cudaMemcpyAsync(dev, host, (size_t)n * F * sizeof(float), cudaMemcpyHostToDevice, st);
+    return cudaMemcpy2DAsync(dev, ld * sizeof(float), host, F * sizeof(float), F * sizeof(float), n,
+                             cudaMemcpyHostToDevice, st);
+}
+
+static cudaError_t copy_out(float* host, const float* dev, int64_t n, int64_t ld, int64_t F, cudaStream_t st) {
+    if (ld == F) return cudaMemcpyAsync(host, dev, (size_t)n * F * sizeof(float), cudaMemcpyDeviceToHost, st);
+    return cudaMemcpy2DAsync(host, F * sizeof(float), dev, ld * sizeof(float), F * sizeof(float), n,
+                             cudaMemcpyDeviceToHost, st);
+}
+
 extern "C" int gnntf_appnp_propagate_host_f32(const gnntf_csr_t* A, const float* H0_host,
                                               float* out_host, float* dev_H0, float* dev_out,
                                               float* dev_scratch, int64_t ld, int64_t F, double alpha,
@@ -148,20 +162,81 @@ extern "C" int gnntf_appnp_propagate_host_f32(const gnntf_csr_t* A, const float*
     if (n == 0 || F == 0) return GNNTF_OK;
     if (H0_host == nullptr || out_host == nullptr || dev_H0 == nullptr || dev_out == nullptr)
         return GNNTF_E_NULL;
-    if (ld == F) {  // dense on both sides: one linear DMA (2-D copies are issued row by row)
-        GNNTF_CUDA_TRY(cudaMemcpyAsync(dev_H0, H0_host, (size_t)n * F * sizeof(float), cudaMemcpyHostToDevice, st));
-    } else {
-        GNNTF_CUDA_TRY(cudaMemcpy2DAsync(dev_H0, ld * sizeof(float), H0_host, F * sizeof(float),
-                                         F * sizeof(float), n, cudaMemcpyHostToDevice, st));
-    }
+    GNNTF_CUDA_TRY(copy_in(dev_H0, H0_host, n, ld, F, st));
     int rc = propagate_impl(A, 1, K, dev_H0, dev_out, dev_scratch, ld, F, alpha, st);
     if (rc != GNNTF_OK) return rc;
-    if (ld == F) {
-        GNNTF_CUDA_TRY(cudaMemcpyAsync(out_host, dev_out, (size_t)n * F * sizeof(float), cudaMemcpyDeviceToHost, st));
-    } else {
-        GNNTF_CUDA_TRY(cudaMemcpy2DAsync(out_host, F * sizeof(float), dev_out, ld * sizeof(float),
-                                         F * sizeof(float), n, cudaMemcpyDeviceToHost, st));
+    GNNTF_CUDA_TRY(copy_out(out_host, dev_out, n, ld, F, st));
+    return GNNTF_OK;
+}
+
+// Several feature matrices through the same adjacency, software-pipelined over three streams: while the
+// K steps of matrix b run on the caller's stream, matrix b+1 travels host -> device on a copy stream and
+// the result of matrix b-1 travels device -> host on another (PCIe is full duplex, and the copy engines
+// do not take SMs).  Two device slots {H0, out} alternate; the scratch is shared (the K-step chains are
+// serialised on the caller's stream).  Ordering per slot s = b & 1:
+//   H2D(b)     after compute(b-2)   (the slot's H0 is free)
+//   compute(b) after H2D(b) and D2H(b-2)  (the slot's out is free)
+//   D2H(b)     after compute(b)
+// The caller's stream finally waits for the last two read-backs, so synchronising it is enough.
+namespace {
+struct HostPipeline {
+    cudaStream_t up = nullptr, down = nullptr;
+    cudaEvent_t start = nullptr, in[2] = {nullptr, nullptr}, comp[2] = {nullptr, nullptr}, out[2] = {nullptr, nullptr};
+    cudaError_t create() {
+        cudaError_t e;
+        if ((e = cudaStreamCreateWithFlags(&up, cudaStreamNonBlocking)) != cudaSuccess) return e;
+        if ((e = cudaStreamCreateWithFlags(&down, cudaStreamNonBlocking)) != cudaSuccess) return e;
+        cudaEvent_t* all[] = {&start, &in[0], &in[1], &comp[0], &comp[1], &out[0], &out[1]};
+        for (cudaEvent_t* ev : all)
+            if ((e = cudaEventCreateWithFlags(ev, cudaEventDisableTiming)) != cudaSuccess) return e;
+        return cudaSuccess;
     }
+    ~HostPipeline() {  // destroying a stream / event with work in flight is deferred by the runtime
+        cudaEvent_t all[] = {start, in[0], in[1], comp[0], comp[1], out[0], out[1]};
+        for (cudaEvent_t ev : all)
+            if (ev) cudaEventDestroy(ev);
+        if (up) cudaStreamDestroy(up);
+        if (down) cudaStreamDestroy(down);
+    }
+};
+}  // namespace
+
+extern "C" int gnntf_appnp_propagate_host_batched_f32(const gnntf_csr_t* A, const float* const* H0_host,
+                                                      float* const* out_host, int n_batches, float* dev_work,
+                                                      int64_t ld, int64_t F, double alpha, int K, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (A == nullptr) return GNNTF_E_NULL;
+    const int64_t n = A->n_rows;
+    if (F < 0 || ld < F || n_batches < 0) return GNNTF_E_SIZE;
+    if (n == 0 || F == 0 || n_batches == 0) return GNNTF_OK;
+    if (H0_host == nullptr || out_host == nullptr || dev_work == nullptr) return GNNTF_E_NULL;
+    for (int b = 0; b < n_batches; ++b)
+        if (H0_host[b] == nullptr || out_host[b] == nullptr) return GNNTF_E_NULL;
+    const size_t mat = (size_t)n * (size_t)ld;
+    float* dev_H0[2] = {dev_work, dev_work + 2 * mat};
+    float* dev_out[2] = {dev_work + mat, dev_work + 3 * mat};
+    float* dev_scratch = dev_work + 4 * mat;
+    HostPipeline p;
+    GNNTF_CUDA_TRY(p.create());
+    GNNTF_CUDA_TRY(cudaEventRecord(p.start, st));  // the copies start after what the caller enqueued before
+    GNNTF_CUDA_TRY(cudaStreamWaitEvent(p.up, p.start, 0));
+    GNNTF_CUDA_TRY(cudaStreamWaitEvent(p.down, p.start, 0));
+    for (int b = 0; b < n_batches; ++b) {
+        const int s = b & 1;
+        if (b >= 2) GNNTF_CUDA_TRY(cudaStreamWaitEvent(p.up, p.comp[s], 0));
+        GNNTF_CUDA_TRY(copy_in(dev_H0[s], H0_host[b], n, ld, F, p.up));
+        GNNTF_CUDA_TRY(cudaEventRecord(p.in[s], p.up));
+        GNNTF_CUDA_TRY(cudaStreamWaitEvent(st, p.in[s], 0));
+        if (b >= 2) GNNTF_CUDA_TRY(cudaStreamWaitEvent(st, p.out[s], 0));
+        int rc = propagate_impl(A, 1, K, dev_H0[s], dev_out[s], dev_scratch, ld, F, alpha, st);
+        if (rc != GNNTF_OK) return rc;
+        GNNTF_CUDA_TRY(cudaEventRecord(p.comp[s], st));
+        GNNTF_CUDA_TRY(cudaStreamWaitEvent(p.down, p.comp[s], 0));
+        GNNTF_CUDA_TRY(copy_out(out_host[b], dev_out[s], n, ld, F, p.down));
+        GNNTF_CUDA_TRY(cudaEventRecord(p.out[s], p.down));
+    }
+    GNNTF_CUDA_TRY(cudaStreamWaitEvent(st, p.out[(n_batches - 1) & 1], 0));
+    if (n_batches >= 2) GNNTF_CUDA_TRY(cudaStreamWaitEvent(st, p.out[n_batches & 1], 0));
     return GNNTF_OK;
 }
 

@@ -8,7 +8,7 @@ from .nn import (Activation, Concatenate, Dense, Dropout, Layer, Layered, Predic
                  WrappedVariable)
 from .gnn import (APPNP, GCN, GCNII, GCNIILayer, GCNIISpectralPreservingLayer, GCNLayer, GCNSpectralPreservingLayer, GNN,
                   NGCF, NGCFLayer, NodeClassification, PPRIteration, Structural)
-from .ops import (appnp_propagate, appnp_propagate_host, appnp_step, bias_act_dropout, node_cross_entropy,
+from .ops import (appnp_propagate, appnp_propagate_host, appnp_propagate_host_batched, appnp_step, bias_act_dropout, node_cross_entropy,
                   sparse_dense_matmul)
 from .sparse import NormalizedAdjacency, SparseAdjacency
 

@@ -279,15 +279,18 @@ class ShardedPropagator:
         self.parts, col0, self._shared = [], 0, []
         self._opened, self._flags, self._closed = [], None, False
         self.use_graph, self._graphs, self._graph_error = True, {}, None
+        from .ops import pitch_for
         for w in widths:
             if self.push:
-                mats = [_SharedBuffer((n_ext, w), torch.float32, dev) for _ in range(2)]
+                ld = pitch_for(w)   # rows are gathered whole: a 128-byte-aligned pitch when that saves lines (ops.pitch_for)
+                mats = [_SharedBuffer((n_ext, ld), torch.float32, dev) for _ in range(2)]
                 self._shared.append(mats)
                 bufs = [m.tensor for m in mats]
             else:
+                ld = w
                 bufs = [torch.zeros((n_ext, w), dtype=torch.float32, device=dev) for _ in range(2)]
-            self.parts.append(dict(F=w, col0=col0, buf=bufs, send=None, n_send=n_send,   # send buffer: NCCL path only
-                                   H0=torch.empty((self.n_local, w), dtype=torch.float32, device=dev), work=None))
+            self.parts.append(dict(F=w, ld=ld, col0=col0, buf=bufs, send=None, n_send=n_send,   # send buffer: NCCL path only
+                                   H0=torch.zeros((self.n_local, ld), dtype=torch.float32, device=dev), work=None))
             col0 += w
         if self.push:
             # flags[0, q]: epoch of the last push received from rank q; flags[1, q]: rank q's end-of-propagation ack
@@ -406,10 +409,10 @@ class ShardedPropagator:
         nat, L, p = self.nat, self.nat.lib(), self.plan
         pi = self.parts.index(part)
         bi = 0 if src.data_ptr() == part["buf"][0].data_ptr() else 1
-        F = part["F"]
-        nat.check(L.gnntf_halo_push_signal_f32(nat.ptr(src), F, nat.ptr(p.send_idx), nat.ptr(self._send_off),
+        F, ld = part["F"], part["ld"]
+        nat.check(L.gnntf_halo_push_signal_f32(nat.ptr(src), ld, nat.ptr(p.send_idx), nat.ptr(self._send_off),
                                                nat.ptr(self._peer_ptrs[pi][bi]), nat.ptr(self._peer_row0), p.world,
-                                               int(p.send_idx.numel()), self._rotate, F, F, nat.ptr(self._done),
+                                               int(p.send_idx.numel()), self._rotate, ld, F, nat.ptr(self._done),
                                                nat.ptr(self._peer_data_flags), p.rank, nat.ptr(self._epoch), int(delta),
                                                nat.stream_ptr()), "halo_push_signal")
 
@@ -419,10 +422,10 @@ class ShardedPropagator:
         nat, L, p = self.nat, self.nat.lib(), self.plan
         pi = self.parts.index(part)
         bi = 0 if src.data_ptr() == part["buf"][0].data_ptr() else 1
-        F = part["F"]
+        F, ld = part["F"], part["ld"]
         s1 = self.owned.struct(self.owned_val, F)
         nat.check(L.gnntf_step_push_f32(ctypes.byref(s1), nat.ptr(src), nat.ptr(part["H0"]) if alpha is not None else None,
-                                        nat.ptr(dst), F, F, float(alpha if alpha is not None else 0.0), nat.ptr(p.send_idx),
+                                        nat.ptr(dst), ld, F, float(alpha if alpha is not None else 0.0), nat.ptr(p.send_idx),
                                         nat.ptr(self._send_off), nat.ptr(self._peer_ptrs[pi][bi]), nat.ptr(self._peer_row0),
                                         p.world, int(p.send_idx.numel()), self._rotate, nat.ptr(self._done),
                                         nat.ptr(self._peer_data_flags), p.rank, nat.ptr(self._epoch), int(delta),
@@ -467,22 +470,22 @@ class ShardedPropagator:
     def _pass1(self, part, src, dst, alpha):
         """Every row over its owned columns; alpha=None: plain SpMM, else the full fused PPR epilogue."""
         nat, L = self.nat, self.nat.lib()
-        F, st = part["F"], self.nat.stream_ptr()
+        F, ld, st = part["F"], part["ld"], self.nat.stream_ptr()
         s1 = self.owned.struct(self.owned_val, F)
         if alpha is None:
-            nat.check(L.gnntf_spmm_f32(ctypes.byref(s1), nat.ptr(src), F, nat.ptr(dst), F, F, st), "spmm")
+            nat.check(L.gnntf_spmm_f32(ctypes.byref(s1), nat.ptr(src), ld, nat.ptr(dst), ld, F, st), "spmm")
         else:
-            nat.check(L.gnntf_appnp_step_f32(ctypes.byref(s1), nat.ptr(src), nat.ptr(part["H0"]), nat.ptr(dst), F, F,
+            nat.check(L.gnntf_appnp_step_f32(ctypes.byref(s1), nat.ptr(src), nat.ptr(part["H0"]), nat.ptr(dst), ld, F,
                                              float(alpha), None, 1.0, nat.ACT_IDENTITY, st), "appnp_step")
 
     def _pass2(self, part, src, dst, alpha):
         """dst[boundary rows] += (1-a) * (entries over halo columns) · H_halo."""
         nat, L = self.nat, self.nat.lib()
         if self.halo_part.n > 0:
-            F = part["F"]
+            F, ld = part["F"], part["ld"]
             s2 = self.halo_part.struct(self.halo_val, F)
             scale = 1.0 if alpha is None else 1.0 - float(alpha)
-            nat.check(L.gnntf_spmm_acc_f32(ctypes.byref(s2), nat.ptr(src), F, nat.ptr(dst), F, F, scale, nat.stream_ptr()),
+            nat.check(L.gnntf_spmm_acc_f32(ctypes.byref(s2), nat.ptr(src), ld, nat.ptr(dst), ld, F, scale, nat.stream_ptr()),
                       "spmm_acc")
 
     def _wait_exchange(self, part):
@@ -551,7 +554,7 @@ class ShardedPropagator:
             return self._propagate_push(H0_local, alpha, iterations)
         cur = []
         for part in self.parts:
-            part["H0"].copy_(H0_local[:, part["col0"]:part["col0"] + part["F"]])
+            part["H0"][:, :part["F"]].copy_(H0_local[:, part["col0"]:part["col0"] + part["F"]])
             src, dst = part["buf"]
             src[:self.n_local].copy_(part["H0"])
             cur.append([src, dst])
@@ -567,8 +570,8 @@ class ShardedPropagator:
                     self._start_exchange(part, pair[0], delta=k + 2)
         self._finish(iterations)
         if len(self.parts) == 1:
-            return cur[0][0][:self.n_local]
-        return torch.cat([pair[0][:self.n_local] for pair in cur], dim=1)
+            return cur[0][0][:self.n_local, :self.parts[0]["F"]]
+        return torch.cat([pair[0][:self.n_local, :part["F"]] for part, pair in zip(self.parts, cur)], dim=1)
 
     def _propagate_push(self, H0_local, alpha, iterations, spmm_only=False):
         """Push mode, ONE stream, per step:  [push of H_k ∥ owned-column pass] -> flag wait -> halo-column pass.
@@ -577,9 +580,9 @@ class ShardedPropagator:
         for part in self.parts:
             if spmm_only:
                 src, dst = part["buf"]
-                src[:self.n_local].copy_(H0_local[:, part["col0"]:part["col0"] + part["F"]])
+                src[:self.n_local, :part["F"]].copy_(H0_local[:, part["col0"]:part["col0"] + part["F"]])
             else:
-                part["H0"].copy_(H0_local[:, part["col0"]:part["col0"] + part["F"]])
+                part["H0"][:, :part["F"]].copy_(H0_local[:, part["col0"]:part["col0"] + part["F"]])
                 src, dst = part["buf"]
                 src[:self.n_local].copy_(part["H0"])
             cur.append([src, dst])
@@ -596,8 +599,8 @@ class ShardedPropagator:
                 pair[0], pair[1] = dst, src
         self._finish(iterations)
         if len(self.parts) == 1:
-            return cur[0][0][:self.n_local]
-        return torch.cat([pair[0][:self.n_local] for pair in cur], dim=1)
+            return cur[0][0][:self.n_local, :self.parts[0]["F"]]
+        return torch.cat([pair[0][:self.n_local, :part["F"]] for part, pair in zip(self.parts, cur)], dim=1)
 
     def spmm(self, H_local):
         """One sharded SpMM ``(Â·H)[lo:hi]`` (BASELINE config 5, the R-MAT sweep): a single halo exchange
@@ -607,10 +610,10 @@ class ShardedPropagator:
         if self.push:
             return self._propagate_push(H_local, None, 1, spmm_only=True)
         src, dst = part["buf"]
-        src[:self.n_local].copy_(H_local)
+        src[:self.n_local, :part["F"]].copy_(H_local)
         self._start_exchange(part, src, delta=1, first=True)
         self._compute(part, src, dst, None)
-        return dst[:self.n_local]
+        return dst[:self.n_local, :part["F"]]
 
     def propagate_host_timed(self, H0_host, alpha, iterations, reps=3):
         """End-to-end: this shard's rows of H0 in pinned host memory -> device, K steps, result shard -> host.
@@ -662,9 +665,9 @@ def propagate_lockstep(props, H0_locals, alpha=0.1, iterations=10, spmm_only=Fal
     for pr, H0 in zip(props, H0_locals):
         part = pr.parts[0]
         if not spmm_only:
-            part["H0"].copy_(H0)
+            part["H0"][:, :part["F"]].copy_(H0)
         src, dst = part["buf"]
-        src[:pr.n_local].copy_(H0)
+        src[:pr.n_local, :part["F"]].copy_(H0)
         cur.append([src, dst])
     K = 1 if spmm_only else iterations
     a = None if spmm_only else alpha
@@ -681,4 +684,4 @@ def propagate_lockstep(props, H0_locals, alpha=0.1, iterations=10, spmm_only=Fal
     for pr in props:
         pr._ack(K)
         pr._epoch.add_(K)
-    return [pair[0][:pr.n_local] for pr, pair in zip(props, cur)]
+    return [pair[0][:pr.n_local, :pr.parts[0]["F"]] for pr, pair in zip(props, cur)]

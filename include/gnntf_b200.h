@@ -197,6 +197,19 @@ int gnntf_appnp_propagate_host_f32(const gnntf_csr_t* A, const float* H0_host, f
                                    float* dev_H0, float* dev_out, float* dev_scratch, int64_t ld,
                                    int64_t F, double alpha, int K, void* stream);
 
+/* n_batches feature matrices through the same adjacency, HOST buffers on both sides, software-pipelined:
+ * while the K steps of matrix b run on `stream`, matrix b+1 is copied host -> device and the result of
+ * matrix b-1 device -> host on two internal copy streams (PCIe is full duplex).  H0_host / out_host: HOST
+ * arrays of n_batches host pointers (n_rows*F floats each, dense, pinned for full speed; the same pointer
+ * may appear several times in H0_host, and in out_host if the caller does not need every result).
+ * dev_work: 5*n_rows*ld floats of device memory (two {H0, out} slots and one scratch).  On return `stream`
+ * waits for the last read-back: synchronising it is enough.  Results are those of n_batches calls of
+ * gnntf_appnp_propagate_host_f32 (the serving form of Layered.__call__, gnntf/core/nn/layered.py:52-55,
+ * applied to a sequence of inputs). */
+int gnntf_appnp_propagate_host_batched_f32(const gnntf_csr_t* A, const float* const* H0_host,
+                                           float* const* out_host, int n_batches, float* dev_work,
+                                           int64_t ld, int64_t F, double alpha, int K, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * The element-wise stages on either side of the path, fused (callers of the propagation).
  *

@@ -33,7 +33,7 @@ def timed(fn, reps=10, warm=3):
 
 
 def main():
-    cases = [(int(w), 100) for w in (sys.argv[1:] or ["2", "4"])] + [(4, 52)]
+    cases = [(int(w), 100) for w in (sys.argv[1:] or ["2", "4"])] + [(4, 52), (4, 64), (4, 48)]
     n, edges = synthetic.shaped_edges("products", seed=0, device="cuda")
     adj = gnntf.edges2adj(edges, None, n)
     A = adj.normalized("symmetric")

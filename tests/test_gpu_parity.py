@@ -475,6 +475,30 @@ def test_host_buffer_entry_matches_device_entry():
     assert torch.equal(out_host, out_dev.cpu())
 
 
+@pytest.mark.parametrize("n_batches,F,K", [(1, 47, 10), (2, 40, 3), (5, 100, 10), (7, 16, 1)])
+def test_host_batched_pipeline_matches_single_calls(n_batches, F, K):
+    """gnntf_appnp_propagate_host_batched_f32 (three-stream software pipeline, two device slots): every
+    result is bit-equal to the device entry on the same input, for odd / even batch counts, repeated
+    input pointers and a caller-provided workspace; the call before and after on the same stream stay ordered."""
+    gnntf = _gnntf()
+    n, e = 30000, 400000
+    edges, w = _random_edges(n, e, seed=17)
+    adj = gnntf.edges2adj(edges, w, n)
+    A = adj.normalized("symmetric")
+    ins = [torch.randn((n, F)).pin_memory() for _ in range(min(n_batches, 3))]
+    seq = [ins[b % len(ins)] for b in range(n_batches)]                      # pointers repeat from batch 3 on
+    work = torch.full((5, n, F), float("nan"), device="cuda")
+    outs = gnntf.appnp_propagate_host_batched(A, seq, 0.1, K, work=work)
+    assert len(outs) == n_batches
+    for H, got in zip(seq, outs):
+        assert torch.equal(got, gnntf.appnp_propagate(A, H.cuda(), 0.1, K).cpu())
+    again = gnntf.appnp_propagate_host_batched(A, seq, 0.1, K)                # own workspace, own outputs
+    assert all(torch.equal(x, y) for x, y in zip(outs, again))
+    assert gnntf.appnp_propagate_host_batched(A, [], 0.1, K) == []
+    with pytest.raises(ValueError):
+        gnntf.appnp_propagate_host_batched(A, [seq[0].cuda()], 0.1, K)
+
+
 # ------------------------------------------------------------------------------------------
 # Row-sharded path: all ranks emulated in ONE process on one GPU (the exchange is a device copy),
 # native pack + interior/boundary step kernels with row_map.  The NCCL exchange itself is covered
