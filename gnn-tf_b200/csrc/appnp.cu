@@ -59,10 +59,12 @@ static int propagate_impl(const gnntf_csr_t* A_k, int n_adj, int K, const float*
         return GNNTF_OK;
     }
     if (K > 1 && scratch == nullptr && n > 0 && F > 0) return GNNTF_E_NULL;
-    if (n_adj == 1 && K > 1) {  // launch-bound shapes: all K steps in one cooperative launch
+    if (n_adj == 1 && K > 1) {  // launch-bound shapes: all K steps in one cluster launch / one cooperative launch
         int rc = validate_csr(&A_k[0]);
         if (rc != GNNTF_OK) return rc;
         bool taken = false;
+        rc = appnp_cluster_propagate(&A_k[0], H0, H_out, ld, F, alpha, K, 0, 0, st, &taken);
+        if (rc != GNNTF_OK || taken) return rc;
         rc = spmm_persistent_propagate(&A_k[0], H0, H_out, scratch, ld, F, alpha, K, st, &taken);
         if (rc != GNNTF_OK || taken) return rc;
     }
@@ -250,6 +252,7 @@ extern "C" const char* gnntf_status_str(int code) {
         case GNNTF_E_MODE: return "Invalid matrix normalization";
         case GNNTF_E_WORKSPACE: return "workspace too small";
         case GNNTF_E_ALIGN: return "pointer misaligned (coo_indices must be 16-byte aligned)";
+        case GNNTF_E_SHAPE: return "shape does not qualify for this specialised entry point";
         default: break;
     }
     if (code > 0) return cudaGetErrorString((cudaError_t)code);

@@ -34,4 +34,9 @@ int validate_csr(const gnntf_csr_t* A);
 int spmm_persistent_propagate(const gnntf_csr_t* A, const float* H0, float* H_out, float* scratch, int64_t ld,
                               int64_t F, double alpha, int K, cudaStream_t st, bool* taken);
 
+// The same K steps with the whole problem resident in the shared memory of one thread-block cluster
+// (cluster.cu); cluster_size / threads 0 = choose.  *taken false: the shape does not qualify.
+int appnp_cluster_propagate(const gnntf_csr_t* A, const float* H0, float* H_out, int64_t ld, int64_t F, double alpha,
+                            int K, int cluster_size, int threads, cudaStream_t st, bool* taken);
+
 }  // namespace gnntf

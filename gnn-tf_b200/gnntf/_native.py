@@ -16,6 +16,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("GNNTF_B200_LIB") or os.path.join(_HERE, "_lib", "libgnntf_b200.so")
 
 GNNTF_OK = 0
+GNNTF_E_SHAPE = -6   # a specialised entry point declined the shape (nothing was enqueued)
 NORM = {"symmetric": 0, "bipartite": 1, "none": 2}
 EYE = {"none": 0, "before": 1, "after": 2}
 ACT_IDENTITY, ACT_RELU, ACT_LEAKY_RELU = 0, 1, 2
@@ -25,7 +26,7 @@ SYMBOLS = [
     "gnntf_abi_version", "gnntf_status_str", "gnntf_csr_build_ws_bytes", "gnntf_csr_build",
     "gnntf_normalize_f32", "gnntf_arrange_sweep_f32", "gnntf_spmm_plan_count", "gnntf_spmm_plan_fill", "gnntf_spmm_f32", "gnntf_spmm_acc_f32",
     "gnntf_appnp_step_f32", "gnntf_appnp_propagate_f32", "gnntf_appnp_propagate_multi_f32",
-    "gnntf_appnp_propagate_bwd_f32", "gnntf_appnp_propagate_host_f32", "gnntf_appnp_propagate_host_batched_f32",
+    "gnntf_appnp_propagate_bwd_f32", "gnntf_appnp_propagate_host_f32", "gnntf_appnp_propagate_host_batched_f32", "gnntf_appnp_propagate_cluster_f32",
     "gnntf_halo_pack_f32", "gnntf_halo_push_f32", "gnntf_ipc_alloc", "gnntf_ipc_open", "gnntf_ipc_close", "gnntf_ipc_free",
     "gnntf_halo_push_signal_f32", "gnntf_step_push_f32", "gnntf_flags_wait", "gnntf_flags_signal",
     "gnntf_bias_act_dropout_f32", "gnntf_bias_act_dropout_bwd_f32", "gnntf_node_xent_f32", "gnntf_node_xent_bwd_f32",
@@ -87,6 +88,8 @@ def lib():
                                                 c_int64, c_int64, c_double, c_void_p]
     L.gnntf_appnp_propagate_host_f32.argtypes = [POINTER(CsrStruct), c_void_p, c_void_p, c_void_p, c_void_p,
                                                  c_void_p, c_int64, c_int64, c_double, c_int, c_void_p]
+    L.gnntf_appnp_propagate_cluster_f32.argtypes = [POINTER(CsrStruct), c_void_p, c_void_p, c_int64, c_int64, c_double,
+                                                    c_int, c_int, c_int, c_void_p]
     L.gnntf_appnp_propagate_host_batched_f32.argtypes = [POINTER(CsrStruct), c_void_p, c_void_p, c_int, c_void_p,
                                                          c_int64, c_int64, c_double, c_int, c_void_p]
     L.gnntf_halo_pack_f32.argtypes = [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_int64, c_void_p]

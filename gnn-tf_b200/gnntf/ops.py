@@ -192,6 +192,22 @@ def propagate_raw(adjs, H0, alpha, K, out=None, scratch=None):
     return out
 
 
+def propagate_cluster_raw(adj, H0, alpha, K, cluster_size=0, threads=0, out=None):
+    """The K steps in ONE thread-block-cluster launch with the graph and the features resident in the
+    cluster's shared memory (gnntf_appnp_propagate_cluster_f32; Cora / PubMed-sized problems only — the general
+    entry takes this path by itself when the shape qualifies).  Returns None when the shape does not qualify."""
+    L = nat.lib()
+    F, ld = H0.shape[1], _ld(H0)
+    out = out if out is not None else torch.empty_like(H0)
+    s = adj.struct(F)
+    rc = L.gnntf_appnp_propagate_cluster_f32(ctypes.byref(s), nat.ptr(H0), nat.ptr(out), ld, F, float(alpha), int(K),
+                                             int(cluster_size), int(threads), nat.stream_ptr())
+    if rc == nat.GNNTF_E_SHAPE:
+        return None
+    nat.check(rc, "appnp_propagate_cluster")
+    return out
+
+
 class _Propagate(torch.autograd.Function):
     @staticmethod
     def forward(ctx, adjs, H0, alpha, K):

@@ -44,6 +44,7 @@ extern "C" {
 #define GNNTF_E_MODE (-3)      /* "Invalid matrix normalization" (gnn.py:46-47) or bad enum */
 #define GNNTF_E_WORKSPACE (-4) /* workspace too small */
 #define GNNTF_E_ALIGN (-5)     /* pointer misaligned (coo_indices of gnntf_csr_build: 16 bytes) */
+#define GNNTF_E_SHAPE (-6)     /* the shape does not qualify for this specialised entry (use the general one) */
 
 /* normalized= of GNN.get_adjacency (gnn.py:36) */
 #define GNNTF_NORM_SYMMETRIC 0 /* D = 1/sqrt(colsum); v*D[row]*D[col]   gnn.py:40-42 */
@@ -176,6 +177,18 @@ int gnntf_appnp_step_f32(const gnntf_csr_t* A, const float* H_in, const float* H
  * scratch: n_rows*ld floats (ping-pong partner of H_out).  H0, H_out, scratch must be distinct. */
 int gnntf_appnp_propagate_f32(const gnntf_csr_t* A, const float* H0, float* H_out, float* scratch,
                               int64_t ld, int64_t F, double alpha, int K, void* stream);
+
+/* The same K steps inside ONE thread-block-cluster launch: the cluster's CTAs keep their rows of the two
+ * ping-pong feature matrices, of H0 and of the CSR in shared memory for the whole call, gather neighbour
+ * rows through distributed shared memory and meet at a hardware cluster barrier between steps — global
+ * memory is read once and written once.  For graphs the size of Cora / PubMed (n_rows*F*12 bytes plus the
+ * CSR must fit the cluster's shared memory, F <= 128, F % 4 == 0, ld % 4 == 0, no split rows, 16-byte
+ * aligned bases); results are bit-identical to gnntf_appnp_propagate_f32, which takes this path by
+ * itself when the shape qualifies.  cluster_size: 0 = choose, else 1, 2, 4, 8 or 16 CTAs; threads: 0 = choose,
+ * else 512 or 1024 per CTA.
+ * Returns GNNTF_E_SHAPE when the shape does not qualify (nothing was enqueued).  No scratch needed. */
+int gnntf_appnp_propagate_cluster_f32(const gnntf_csr_t* A, const float* H0, float* H_out, int64_t ld,
+                                      int64_t F, double alpha, int K, int cluster_size, int threads, void* stream);
 
 /* Training-mode forward: step k uses its own adjacency A_k[k] (own edge mask, filter.py:18). */
 int gnntf_appnp_propagate_multi_f32(const gnntf_csr_t* A_k, int K, const float* H0, float* H_out,

@@ -745,6 +745,63 @@ def test_persistent_k_step_kernel_equals_step_by_step(shape, F):
     assert np.array_equal(_np(fused), expect), "no split rows, unit weights: bit-identical to the oracle"
 
 
+@pytest.mark.parametrize("shape,F,K", [("cora", 8, 10), ("cora", 8, 1), ("cora", 12, 3), ("cora", 64, 2), ("pubmed", 4, 10),
+                                       ("pubmed", 16, 3), ("cora", 128, 2)])
+def test_cluster_resident_kernel_equals_step_by_step(shape, F, K):
+    """gnntf_appnp_propagate_cluster_f32: graph, features and teleport rows resident in the shared memory of one
+    thread-block cluster for all K steps, neighbour rows gathered through distributed shared memory.  Every
+    cluster size / CTA size that can hold the shape must be bit-identical to K separate fused-step launches."""
+    gnntf = _gnntf()
+    from gnntf import ops
+    n, e, _, _ = synthetic.SHAPES[shape]
+    G = synthetic.citation_graph(n, e, seed=0)
+    adj = gnntf.graph2adj(G)
+    A = adj.normalized("symmetric")
+    H0 = synthetic.features(n, F, seed=1, device="cuda")
+    H = H0
+    for _ in range(K):
+        H = gnntf.appnp_step(A, H, H0, 0.1)
+    ran = 0
+    for C in (0, 1, 2, 4, 8, 16):
+        for threads in (0, 512, 1024):
+            got = ops.propagate_cluster_raw(A, H0, 0.1, K, C, threads, out=torch.full_like(H0, float("nan")))
+            if got is None:
+                continue
+            ran += 1
+            assert torch.equal(got, H), f"cluster of {C} CTAs x {threads} threads"
+    assert ran >= 3, ran
+    # shapes that cannot be resident are declined, not mangled
+    big_n, big_edges = synthetic.shaped_edges("arxiv", seed=0, device="cuda", scale=0.5)
+    big = gnntf.edges2adj(big_edges, None, big_n).normalized("symmetric")
+    assert ops.propagate_cluster_raw(big, synthetic.features(big_n, 64, 1, "cuda"), 0.1, 3) is None
+
+
+def test_cluster_resident_kernel_hub_rows_and_spilled_slices():
+    """Weighted graph with a few hub rows just under the split threshold and very uneven slices: the CTA
+    owning the hubs holds more entries than its shared-memory slice, so its tail is read from global memory."""
+    gnntf = _gnntf()
+    from gnntf import ops
+    rng = np.random.default_rng(5)
+    n = 6000
+    hubs = np.stack([np.repeat(np.arange(3), 120), rng.integers(3, n, 360)], 1)
+    rest = rng.integers(0, n, (9000, 2))
+    edges = np.concatenate([hubs, rest[rest[:, 0] != rest[:, 1]]]).astype(np.int64)
+    w = rng.uniform(0.5, 2.0, len(edges)).astype(np.float32)
+    adj = gnntf.edges2adj(torch.from_numpy(edges).cuda(), torch.from_numpy(w).cuda(), n)
+    assert adj.csr.n_long == 0
+    A = adj.normalized("symmetric")
+    for F in (8, 32):
+        H0 = synthetic.features(n, F, seed=2, device="cuda")
+        H = H0
+        for _ in range(3):
+            H = gnntf.appnp_step(A, H, H0, 0.1)
+        for C in (2, 8, 16):
+            got = ops.propagate_cluster_raw(A, H0, 0.1, 3, C, 0)
+            if got is not None:
+                assert torch.equal(got, H), (F, C)
+        assert torch.equal(gnntf.appnp_propagate(A, H0, 0.1, 3), H)
+
+
 def test_propagation_is_bitwise_deterministic():
     """No float atomics on the undirected path: two runs (and a rebuilt adjacency) give identical bits,
     including rows split into pieces and the backward pass."""
