@@ -196,6 +196,23 @@ extern "C" int gnntf_flags_signal(int32_t* const* peer_flags, int n_peers, int m
     return GNNTF_OK;
 }
 
+// Copy-engine exchange: this rank's block of rows goes to a peer's buffer as ONE DMA copy over NVLink, followed
+// (same stream, hence after the rows have landed) by a 4-byte DMA copy of the epoch value into the peer's flag
+// slot.  No SM, no L1TEX and no shared-memory traffic: the SpMM running next to it keeps the whole gather path.
+extern "C" int gnntf_peer_copy_signal(void* dst, const void* src, size_t bytes, int32_t* peer_flag,
+                                      const int32_t* epoch_value, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (bytes > 0) {
+        if (dst == nullptr || src == nullptr) return GNNTF_E_NULL;
+        GNNTF_CUDA_TRY(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, st));
+    }
+    if (peer_flag != nullptr) {
+        if (epoch_value == nullptr) return GNNTF_E_NULL;
+        GNNTF_CUDA_TRY(cudaMemcpyAsync(peer_flag, epoch_value, sizeof(int32_t), cudaMemcpyDefault, st));
+    }
+    return GNNTF_OK;
+}
+
 static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
 
 extern "C" int gnntf_ipc_alloc(size_t bytes, void** dev_ptr, unsigned char handle[64]) {

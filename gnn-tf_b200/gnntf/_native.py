@@ -28,7 +28,7 @@ SYMBOLS = [
     "gnntf_appnp_step_f32", "gnntf_appnp_propagate_f32", "gnntf_appnp_propagate_multi_f32",
     "gnntf_appnp_propagate_bwd_f32", "gnntf_appnp_propagate_host_f32", "gnntf_appnp_propagate_host_batched_f32", "gnntf_appnp_propagate_cluster_f32",
     "gnntf_halo_pack_f32", "gnntf_halo_push_f32", "gnntf_ipc_alloc", "gnntf_ipc_open", "gnntf_ipc_close", "gnntf_ipc_free",
-    "gnntf_halo_push_signal_f32", "gnntf_step_push_f32", "gnntf_flags_wait", "gnntf_flags_signal",
+    "gnntf_halo_push_signal_f32", "gnntf_step_push_f32", "gnntf_flags_wait", "gnntf_flags_signal", "gnntf_peer_copy_signal",
     "gnntf_bias_act_dropout_f32", "gnntf_bias_act_dropout_bwd_f32", "gnntf_node_xent_f32", "gnntf_node_xent_bwd_f32",
 ]
 
@@ -95,6 +95,7 @@ def lib():
     L.gnntf_halo_pack_f32.argtypes = [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_int64, c_void_p]
     L.gnntf_halo_push_f32.argtypes = [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int64, c_int64,
                                       c_int64, c_int64, c_void_p]
+    L.gnntf_peer_copy_signal.argtypes = [c_void_p, c_void_p, ctypes.c_size_t, c_void_p, c_void_p, c_void_p]
     L.gnntf_halo_push_signal_f32.argtypes = [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int64, c_int64,
                                              c_int64, c_int64, c_void_p, c_void_p, c_int, c_void_p, c_int32, c_void_p]
     L.gnntf_step_push_f32.argtypes = [POINTER(CsrStruct), c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_double, c_void_p,

@@ -252,7 +252,8 @@ class ShardedPropagator:
     using CUDA IPC (single-GPU emulation of the ranks for tests: :func:`connect_local`,
     :func:`propagate_lockstep`)."""
 
-    def __init__(self, adj, A, F, rank, world, group=None, plan=None, exchange=None, halves=None, push=True, peers="ipc"):
+    def __init__(self, adj, A, F, rank, world, group=None, plan=None, exchange=None, halves=None, push=True, peers="ipc",
+                 copy=False):
         from . import _native as nat
         from .sparse import CsrStructure
         self.nat = nat
@@ -266,6 +267,13 @@ class ShardedPropagator:
         dev = p.row_ptr.device
 
         (o_rp, o_col, o_val), (h_rp, h_col, h_val), h_rows = split_by_column(p.row_ptr, p.col_idx, p.val, self.n_local)
+        # copy-engine exchange: every rank's buffers hold ALL rows (own block at its global offset), columns stay global
+        self.copy = bool(copy) and bool(push) and p.world > 1 and exchange is None
+        self.n_total = int(p.bounds[-1])
+        self.row0 = p.lo if self.copy else 0          # first owned row inside the feature buffers
+        if self.copy:
+            o_col = (o_col + p.lo).to(torch.int32).contiguous()
+            h_col = p.halo_cols[h_col.long() - self.n_local].to(torch.int32).contiguous()
         self.owned, self.owned_val = CsrStructure(self.n_local, o_rp, o_col, None), o_val
         self.halo_part, self.halo_val = CsrStructure(int(h_rows.numel()), h_rp, h_col, None), h_val
         self.halo_part.row_map = h_rows
@@ -274,7 +282,10 @@ class ShardedPropagator:
             halves = 1  # column-half pipelining measured slower than the column split at N=2
         first = ((self.F + halves - 1) // halves + 3) // 4 * 4 if halves > 1 else self.F
         widths = [first, self.F - first] if halves > 1 and self.F - first > 0 else [self.F]
-        n_ext, n_send = self.n_local + self.n_halo, int(sum(p.send_counts))
+        n_ext, n_send = (self.n_total if self.copy else self.n_local + self.n_halo), int(sum(p.send_counts))
+        if self.copy:
+            halves = 1
+            widths = [self.F]
         self.push = bool(push) and p.world > 1 and exchange is None
         self.parts, col0, self._shared = [], 0, []
         self._opened, self._flags, self._closed = [], None, False
@@ -297,6 +308,10 @@ class ShardedPropagator:
             self._flags = _SharedBuffer((2, p.world), torch.int32, dev)
             self._epoch = torch.zeros(1, dtype=torch.int32, device=dev)
             self._done = torch.zeros(1, dtype=torch.int32, device=dev)
+            self._arange = torch.arange(1024, dtype=torch.int32, device=dev)
+            self._epoch_vals = torch.zeros(1024, dtype=torch.int32, device=dev)   # epoch_base + d, refreshed per propagation
+            self._copy_streams = ([torch.cuda.Stream() for _ in range(p.world - 1)]
+                                  if (self.copy and peers == "ipc" and torch.cuda.is_available()) else None)
         if self.push and peers == "ipc":
             # every rank of the row group must take the same path: agree on whether IPC mapping worked
             try:
@@ -307,6 +322,8 @@ class ShardedPropagator:
             flag = torch.tensor([ok], dtype=torch.float32, device=dev)
             dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.group)
             if flag.item() < 1.0:
+                if self.copy:
+                    raise RuntimeError(f"copy-engine exchange needs CUDA IPC peer mappings: {getattr(self, '_map_error', None)}")
                 self.push = False  # the shared buffers are ordinary device memory for the NCCL path
         if not self.push:
             for part in self.parts:
@@ -337,15 +354,19 @@ class ShardedPropagator:
         # my rows land in peer q's halo region after the rows of lower-ranked owners
         row0 = [int(everyone[q]["n_local"]) + int(sum(everyone[q]["recv_counts"][:p.rank])) for q in range(p.world)]
         self._peer_row0 = torch.tensor(row0, dtype=torch.int64, device=dev)
-        self._peer_ptrs = []
+        self._peer_ptrs, self._peer_buf_addr = [], []
         for pi in range(len(self.parts)):
-            per_buf = []
+            per_buf, per_buf_addr = [], []
             for bi in range(2):
-                ptrs = [0 if (q == p.rank or p.send_counts[q] == 0) else buffer_ptr(q, pi, bi) for q in range(p.world)]
+                ptrs = [0 if (q == p.rank or (p.send_counts[q] == 0 and not self.copy)) else buffer_ptr(q, pi, bi)
+                        for q in range(p.world)]
                 per_buf.append(torch.tensor(ptrs, dtype=torch.int64, device=dev))
+                per_buf_addr.append(ptrs)
             self._peer_ptrs.append(per_buf)
+            self._peer_buf_addr.append(per_buf_addr)
         # every peer gets my completion flags (also peers I send no rows to: they wait on all slots)
         fl = [0 if q == p.rank else flags_ptr(q) for q in range(p.world)]
+        self._peer_flag_addr = fl
         self._peer_data_flags = torch.tensor(fl, dtype=torch.int64, device=dev)
         self._peer_ack_flags = torch.tensor([0 if x == 0 else x + 4 * p.world for x in fl], dtype=torch.int64, device=dev)
 
@@ -425,11 +446,73 @@ class ShardedPropagator:
         F, ld = part["F"], part["ld"]
         s1 = self.owned.struct(self.owned_val, F)
         nat.check(L.gnntf_step_push_f32(ctypes.byref(s1), nat.ptr(src), nat.ptr(part["H0"]) if alpha is not None else None,
-                                        nat.ptr(dst), ld, F, float(alpha if alpha is not None else 0.0), nat.ptr(p.send_idx),
+                                        nat.ptr(dst[self.row0:]), ld, F, float(alpha if alpha is not None else 0.0), nat.ptr(p.send_idx),
                                         nat.ptr(self._send_off), nat.ptr(self._peer_ptrs[pi][bi]), nat.ptr(self._peer_row0),
                                         p.world, int(p.send_idx.numel()), self._rotate, nat.ptr(self._done),
                                         nat.ptr(self._peer_data_flags), p.rank, nat.ptr(self._epoch), int(delta),
                                         nat.stream_ptr()), "step_push")
+
+    def _send_block(self, part, src, delta, side_streams=True):
+        """Copy-engine exchange of the step that reads ``src``: this rank's block of rows goes to every peer's
+        buffer as one DMA copy per peer (each on its own stream, ordered after everything enqueued so far on the
+        current stream), followed by a 4-byte DMA of the epoch  base + delta  into the peer's flag slot."""
+        nat, L, p = self.nat, self.nat.lib(), self.plan
+        pi = self.parts.index(part)
+        bi = 0 if src.data_ptr() == part["buf"][0].data_ptr() else 1
+        off = self.lo * part["ld"] * 4
+        nbytes = self.n_local * part["ld"] * 4
+        epoch_value = self._epoch_vals.data_ptr() + 4 * int(delta)
+        ready = None
+        if side_streams and self._copy_streams is not None:
+            ready = torch.cuda.Event()
+            ready.record()
+        for j in range(1, p.world):
+            q = (p.rank + j) % p.world                     # every rank starts with a different destination
+            dst = self._peer_buf_addr[pi][bi][q] + off
+            flag = self._peer_flag_addr[q] + 4 * p.rank
+            if ready is not None:
+                stream = self._copy_streams[j - 1]
+                stream.wait_event(ready)
+                handle = ctypes.c_void_p(stream.cuda_stream)
+            else:
+                handle = nat.stream_ptr()
+            nat.check(L.gnntf_peer_copy_signal(ctypes.c_void_p(dst), ctypes.c_void_p(src.data_ptr() + off), nbytes,
+                                               ctypes.c_void_p(flag), ctypes.c_void_p(epoch_value), handle), "peer_copy_signal")
+
+    def _join_copies(self):
+        if self._copy_streams is not None:
+            cur = torch.cuda.current_stream()
+            for stream in self._copy_streams:
+                ev = torch.cuda.Event()
+                ev.record(stream)
+                cur.wait_event(ev)
+
+    def _propagate_copy(self, H0_local, alpha, iterations, spmm_only=False):
+        """Copy-engine mode, per step:  [DMA of this rank's block of H_k to every peer ∥ owned-column pass] ->
+        flag wait -> halo-column pass.  The buffers hold all rows; this rank's block sits at rows [lo, hi)."""
+        part = self.parts[0]
+        F = part["F"]
+        src, dst = part["buf"]
+        own = slice(self.lo, self.hi)
+        if spmm_only:
+            src[own, :F].copy_(H0_local)
+        else:
+            part["H0"][:, :F].copy_(H0_local)
+            src[own].copy_(part["H0"])
+        if iterations >= self._epoch_vals.numel():
+            raise ValueError("at most 1023 iterations per propagation in copy-engine mode")
+        torch.add(self._arange, self._epoch, out=self._epoch_vals)
+        if iterations > 0:
+            self._wait(1, 0)      # every peer is done reading its buffers of the previous propagation
+        for k in range(iterations):
+            self._send_block(part, src, k + 1)
+            self._pass1(part, src, dst, alpha)
+            self._wait(0, k + 1)
+            self._pass2(part, src, dst, alpha)
+            src, dst = dst, src
+        self._join_copies()
+        self._finish(iterations)
+        return src[own, :F]
 
     def _wait(self, row, delta):
         """Current stream waits until flags[row, q] >= base + delta for every peer q."""
@@ -473,9 +556,9 @@ class ShardedPropagator:
         F, ld, st = part["F"], part["ld"], self.nat.stream_ptr()
         s1 = self.owned.struct(self.owned_val, F)
         if alpha is None:
-            nat.check(L.gnntf_spmm_f32(ctypes.byref(s1), nat.ptr(src), ld, nat.ptr(dst), ld, F, st), "spmm")
+            nat.check(L.gnntf_spmm_f32(ctypes.byref(s1), nat.ptr(src), ld, nat.ptr(dst[self.row0:]), ld, F, st), "spmm")
         else:
-            nat.check(L.gnntf_appnp_step_f32(ctypes.byref(s1), nat.ptr(src), nat.ptr(part["H0"]), nat.ptr(dst), ld, F,
+            nat.check(L.gnntf_appnp_step_f32(ctypes.byref(s1), nat.ptr(src), nat.ptr(part["H0"]), nat.ptr(dst[self.row0:]), ld, F,
                                              float(alpha), None, 1.0, nat.ACT_IDENTITY, st), "appnp_step")
 
     def _pass2(self, part, src, dst, alpha):
@@ -485,7 +568,7 @@ class ShardedPropagator:
             F, ld = part["F"], part["ld"]
             s2 = self.halo_part.struct(self.halo_val, F)
             scale = 1.0 if alpha is None else 1.0 - float(alpha)
-            nat.check(L.gnntf_spmm_acc_f32(ctypes.byref(s2), nat.ptr(src), ld, nat.ptr(dst), ld, F, scale, nat.stream_ptr()),
+            nat.check(L.gnntf_spmm_acc_f32(ctypes.byref(s2), nat.ptr(src), ld, nat.ptr(dst[self.row0:]), ld, F, scale, nat.stream_ptr()),
                       "spmm_acc")
 
     def _wait_exchange(self, part):
@@ -550,6 +633,8 @@ class ShardedPropagator:
         return graph, static_in, out
 
     def _propagate_eager(self, H0_local, alpha, iterations):
+        if self.copy:
+            return self._propagate_copy(H0_local, alpha, iterations)
         if self.push:
             return self._propagate_push(H0_local, alpha, iterations)
         cur = []
@@ -607,6 +692,8 @@ class ShardedPropagator:
         overlapped with the owned-column pass."""
         part = self.parts[0]
         assert len(self.parts) == 1
+        if self.copy:
+            return self._propagate_copy(H_local, None, 1, spmm_only=True)
         if self.push:
             return self._propagate_push(H_local, None, 1, spmm_only=True)
         src, dst = part["buf"]
@@ -667,7 +754,9 @@ def propagate_lockstep(props, H0_locals, alpha=0.1, iterations=10, spmm_only=Fal
         if not spmm_only:
             part["H0"][:, :part["F"]].copy_(H0)
         src, dst = part["buf"]
-        src[:pr.n_local, :part["F"]].copy_(H0)
+        src[pr.row0:pr.row0 + pr.n_local, :part["F"]].copy_(H0)
+        if pr.copy:
+            torch.add(pr._arange, pr._epoch, out=pr._epoch_vals)
         cur.append([src, dst])
     K = 1 if spmm_only else iterations
     a = None if spmm_only else alpha
@@ -675,7 +764,11 @@ def propagate_lockstep(props, H0_locals, alpha=0.1, iterations=10, spmm_only=Fal
         pr._wait(1, 0)
     for k in range(K):
         for pr, (src, dst) in zip(props, cur):
-            pr._step_push(pr.parts[0], src, dst, a, k + 1)      # push of H_k + owned-column pass, one launch
+            if pr.copy:                                          # DMA of the block + flag, then the owned-column pass
+                pr._send_block(pr.parts[0], src, k + 1, side_streams=False)
+                pr._pass1(pr.parts[0], src, dst, a)
+            else:
+                pr._step_push(pr.parts[0], src, dst, a, k + 1)  # push of H_k + owned-column pass, one launch
         for pr, pair in zip(props, cur):
             src, dst = pair
             pr._wait(0, k + 1)
@@ -684,4 +777,4 @@ def propagate_lockstep(props, H0_locals, alpha=0.1, iterations=10, spmm_only=Fal
     for pr in props:
         pr._ack(K)
         pr._epoch.add_(K)
-    return [pair[0][:pr.n_local, :pr.parts[0]["F"]] for pr, pair in zip(props, cur)]
+    return [pair[0][pr.row0:pr.row0 + pr.n_local, :pr.parts[0]["F"]] for pr, pair in zip(props, cur)]

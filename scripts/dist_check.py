@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Multi-GPU correctness check (run under torchrun): the sharded propagation (any ROWSxCOLS grid,
-peer-memory push or NCCL all-to-all) against the single-GPU propagation of the same graph, which
+copy-engine all-gather, peer-memory push kernel or NCCL all-to-all) against the single-GPU propagation of the same graph, which
 every rank computes locally.  Prints PASS/FAIL per rank; exit code 1 on mismatch."""
 import os
 import sys
@@ -18,7 +18,8 @@ rank, local, world = int(os.environ["RANK"]), int(os.environ["LOCAL_RANK"]), int
 torch.cuda.set_device(local)
 dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 grid_arg = sys.argv[1] if len(sys.argv) > 1 else ""
-push = not (len(sys.argv) > 2 and sys.argv[2] == "nccl")
+mode = sys.argv[2] if len(sys.argv) > 2 else "copy"      # copy (copy-engine all-gather) | push (fused push kernel) | nccl
+push = mode != "nccl"
 F = 100
 n, edges = synthetic.shaped_edges("arxiv", seed=0, device="cuda")
 adj = gnntf.edges2adj(edges, None, n)
@@ -26,7 +27,7 @@ A = adj.normalized("symmetric")
 R, C = (int(x) for x in grid_arg.split("x")) if grid_arg else gdist.choose_grid(world, F)
 grid = gdist.Grid2D(rank, world, R, C)
 c0, c1 = gdist.column_range(F, C, grid.c)
-prop = gdist.ShardedPropagator(adj, A, c1 - c0, grid.r, R, group=grid.row_group, push=push)
+prop = gdist.ShardedPropagator(adj, A, c1 - c0, grid.r, R, group=grid.row_group, push=push, copy=(mode == "copy"))
 ok, worst = True, 0.0
 # repeated calls exercise buffer reuse across propagations; odd K with a DIFFERENT H0 per call is the
 # write-after-read hazard of the peer-memory push: a fast rank must not overwrite halo rows
@@ -50,7 +51,7 @@ worst = max(worst, err)
 ok = ok and err < 1e-5
 torch.cuda.synchronize()
 graphs = sum(isinstance(v, tuple) for v in prop._graphs.values())
-print(f"rank {rank} grid {R}x{C} push={prop.push} graphs={graphs} rows {prop.lo}:{prop.hi} cols {c0}:{c1} halo {prop.n_halo} max rel err {worst:.2e} {'PASS' if ok else 'FAIL'}", flush=True)
+print(f"rank {rank} grid {R}x{C} push={prop.push} copy={prop.copy} graphs={graphs} rows {prop.lo}:{prop.hi} cols {c0}:{c1} halo {prop.n_halo} max rel err {worst:.2e} {'PASS' if ok else 'FAIL'}", flush=True)
 flag = torch.tensor([0.0 if ok else 1.0], device="cuda")
 dist.all_reduce(flag)
 prop.close()

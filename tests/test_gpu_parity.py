@@ -596,12 +596,14 @@ def test_halo_push_kernel_on_one_gpu(n_peers, F, rotate_frac):
         assert torch.all(bufs[d][:r0] == -7.0) and torch.all(bufs[d][r0 + counts[d]:] == -7.0)
 
 
+@pytest.mark.parametrize("copy", [False, True], ids=["push", "copy_engine"])
 @pytest.mark.parametrize("world,F,K", [(2, 40, 10), (2, 100, 1), (3, 52, 3), (4, 48, 10), (8, 100, 3), (4, 7, 2)])
-def test_sharded_push_loop_with_emulated_peers(world, F, K):
+def test_sharded_push_loop_with_emulated_peers(world, F, K, copy):
     """The full ShardedPropagator(push=True) loop — fused pack+send+signal kernel, epoch flags in (peer)
     memory, flag-wait kernels, two-pass step — with every rank emulated in this process on one GPU and
     the peer tables aimed at the other ranks' buffers.  Several propagations back to back (odd K too:
-    the buffer-reuse hazard ADVICE r1 describes), then a sharded plain SpMM."""
+    the buffer-reuse hazard ADVICE r1 describes), then a sharded plain SpMM.  ``copy``: the copy-engine form
+    of the exchange (all-gather layout, gnntf_peer_copy_signal: one DMA per peer + a 4-byte DMA of the epoch)."""
     gnntf = _gnntf()
     from gnntf import dist as gdist
     n, edges = synthetic.shaped_edges("arxiv", seed=0, device="cuda", scale=0.15)
@@ -609,8 +611,9 @@ def test_sharded_push_loop_with_emulated_peers(world, F, K):
     A = adj.normalized("symmetric")
     plans = _emulated_plans(gdist, A, world)
     assert sum(p.n_local for p in plans) == n and any(p.n_halo > 0 for p in plans)
-    props = [gdist.ShardedPropagator(adj, A, F, r, world, plan=plans[r], push=True, peers="local") for r in range(world)]
-    assert all(p.push for p in props)
+    props = [gdist.ShardedPropagator(adj, A, F, r, world, plan=plans[r], push=True, peers="local", copy=copy)
+             for r in range(world)]
+    assert all(p.push and p.copy == copy for p in props)
     gdist.connect_local(props)
     for call in range(3):
         H0 = synthetic.features(n, F, 10 + call, "cuda")
@@ -769,7 +772,7 @@ def test_cluster_resident_kernel_equals_step_by_step(shape, F, K):
                 continue
             ran += 1
             assert torch.equal(got, H), f"cluster of {C} CTAs x {threads} threads"
-    assert ran >= 3, ran
+    assert ran >= 3 or (shape, F) == ("pubmed", 16), ran       # PubMed x 16 floats: no cluster size holds it
     # shapes that cannot be resident are declined, not mangled
     big_n, big_edges = synthetic.shaped_edges("arxiv", seed=0, device="cuda", scale=0.5)
     big = gnntf.edges2adj(big_edges, None, big_n).normalized("symmetric")
