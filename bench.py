@@ -292,7 +292,7 @@ def gpu_arm(args):
         grid = gdist.Grid2D(rank, world, R, C)
         c0, c1 = gdist.column_range(F_run, C, grid.c)
         prop = gdist.ShardedPropagator(adj, A, c1 - c0, grid.r, R, group=grid.row_group, halves=args.halves or None,
-                                       push=not args.nccl_exchange, copy=(args.exchange == "copy" and not args.nccl_exchange))
+                                       push=not args.nccl_exchange, copy=({"auto": "auto", "copy": True, "push": False}[args.exchange] if not args.nccl_exchange else False))
         prop.use_graph = not args.no_graph
         log(f"[rank {rank} = row group {grid.r}/{R}, column group {grid.c}/{C}] rows {prop.lo}:{prop.hi} cols {c0}:{c1} "
             f"nnz {prop.nnz_local} halo rows {prop.n_halo} owned-column entries {prop.owned.nnz} "
@@ -523,10 +523,10 @@ def main():
     ap.add_argument("--no-parity", action="store_true", help="skip the post-run check of the result against the C oracle")
     ap.add_argument("--reorder", action="store_true", help="locality-restoring internal node order (gnntf/reorder.py); its cost is part of the build time")
     ap.add_argument("--grid", default="", help="multi-GPU layout ROWSxCOLS (default: gnntf.dist.choose_grid)")
-    ap.add_argument("--exchange", default="copy", choices=["copy", "push"],
+    ap.add_argument("--exchange", default="auto", choices=["auto", "copy", "push"],
                     help="multi-GPU: copy = every rank's block of rows goes to the peers by copy-engine DMA over NVLink "
                          "(all-gather layout, no SM involved); push = the rows each peer references are sent by the leading "
-                         "CTAs of the SpMM launch")
+                         "CTAs of the SpMM launch; auto = copy for row groups of two ranks, push otherwise")
     ap.add_argument("--nccl-exchange", action="store_true", help="multi-GPU: halo rows by NCCL all-to-all instead of the fused peer-memory push")
     ap.add_argument("--halves", type=int, default=0, help="multi-GPU: feature-column chains to pipeline (0 = default)")
     ap.add_argument("--no-graph", action="store_true", help="multi-GPU: launch every step from the host instead of replaying a CUDA graph")

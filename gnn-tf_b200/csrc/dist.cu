@@ -66,6 +66,13 @@ __global__ void signal_flags_kernel(int32_t* const* __restrict__ peer_flags, int
         if (peer_flags[d] != nullptr) st_release_sys(peer_flags[d] + my_slot, epoch);
 }
 
+// *flag = *value at system scope, after everything this GPU wrote before (used behind a copy-engine transfer: the
+// kernel starts only when the copy has completed, the fence + release make the order visible to the peer's acquire)
+__global__ void signal_value_kernel(int32_t* __restrict__ flag, const int32_t* __restrict__ value) {
+    __threadfence_system();
+    st_release_sys(flag, *value);
+}
+
 }  // namespace gnntf
 
 using namespace gnntf;
@@ -196,9 +203,13 @@ extern "C" int gnntf_flags_signal(int32_t* const* peer_flags, int n_peers, int m
     return GNNTF_OK;
 }
 
-// Copy-engine exchange: this rank's block of rows goes to a peer's buffer as ONE DMA copy over NVLink, followed
-// (same stream, hence after the rows have landed) by a 4-byte DMA copy of the epoch value into the peer's flag
-// slot.  No SM, no L1TEX and no shared-memory traffic: the SpMM running next to it keeps the whole gather path.
+// Copy-engine exchange: this rank's block of rows goes to a peer's buffer as ONE DMA copy over NVLink — no SM, no
+// L1TEX and no shared-memory traffic: the SpMM running next to it keeps the whole gather path.  The epoch flag is
+// written by a one-thread kernel enqueued behind the copy (st.release.sys): a kernel behind a copy starts only when
+// the copy has completed.  (The first version wrote the flag with a 4-byte DMA behind the block DMA; it passed at
+// N = 2 and FAILED the parity check at N = 8 (4 x 2, three peers sending at once, errors ~1e-2): stream order between
+// two copies evidently does not make the first one's bytes visible to a polling peer before the second one's.  The
+// kernel form is validated at N = 2, which is where the copy mode is used by default.)
 extern "C" int gnntf_peer_copy_signal(void* dst, const void* src, size_t bytes, int32_t* peer_flag,
                                       const int32_t* epoch_value, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
@@ -208,7 +219,8 @@ extern "C" int gnntf_peer_copy_signal(void* dst, const void* src, size_t bytes, 
     }
     if (peer_flag != nullptr) {
         if (epoch_value == nullptr) return GNNTF_E_NULL;
-        GNNTF_CUDA_TRY(cudaMemcpyAsync(peer_flag, epoch_value, sizeof(int32_t), cudaMemcpyDefault, st));
+        signal_value_kernel<<<1, 1, 0, st>>>(peer_flag, epoch_value);
+        GNNTF_LAUNCH_CHECK();
     }
     return GNNTF_OK;
 }

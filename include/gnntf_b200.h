@@ -307,9 +307,10 @@ int gnntf_flags_signal(int32_t* const* peer_flags, int n_peers, int my_slot, con
 
 /* Copy-engine form of the exchange (all-gather layout: every rank's buffer holds ALL rows, a rank's own block
  * at its global row offset): `bytes` from src (local) to dst (a peer's mapped buffer) as one DMA copy on
- * `stream`, then — stream-ordered after it — a 4-byte DMA copy of *epoch_value (DEVICE int32) into peer_flag
- * (the peer's flag slot for this rank; NULL = no signal).  The consumer acquires the flag with
- * gnntf_flags_wait.  Takes no SM: the SpMM that runs beside it keeps the whole gather path. */
+ * `stream`, then — behind it on the same stream — a one-thread kernel that publishes *epoch_value (DEVICE int32)
+ * into peer_flag with st.release.sys (the peer's flag slot for this rank; NULL = no signal).  The consumer
+ * acquires the flag with gnntf_flags_wait.  The transfer takes no SM: the SpMM that runs beside it keeps the
+ * whole gather path. */
 int gnntf_peer_copy_signal(void* dst, const void* src, size_t bytes, int32_t* peer_flag,
                            const int32_t* epoch_value, void* stream);
 

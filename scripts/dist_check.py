@@ -18,7 +18,7 @@ rank, local, world = int(os.environ["RANK"]), int(os.environ["LOCAL_RANK"]), int
 torch.cuda.set_device(local)
 dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 grid_arg = sys.argv[1] if len(sys.argv) > 1 else ""
-mode = sys.argv[2] if len(sys.argv) > 2 else "copy"      # copy (copy-engine all-gather) | push (fused push kernel) | nccl
+mode = sys.argv[2] if len(sys.argv) > 2 else "auto"      # copy (copy-engine all-gather) | push (fused push kernel) | nccl
 push = mode != "nccl"
 F = 100
 n, edges = synthetic.shaped_edges("arxiv", seed=0, device="cuda")
@@ -27,7 +27,7 @@ A = adj.normalized("symmetric")
 R, C = (int(x) for x in grid_arg.split("x")) if grid_arg else gdist.choose_grid(world, F)
 grid = gdist.Grid2D(rank, world, R, C)
 c0, c1 = gdist.column_range(F, C, grid.c)
-prop = gdist.ShardedPropagator(adj, A, c1 - c0, grid.r, R, group=grid.row_group, push=push, copy=(mode == "copy"))
+prop = gdist.ShardedPropagator(adj, A, c1 - c0, grid.r, R, group=grid.row_group, push=push, copy={"copy": True, "auto": "auto"}.get(mode, False))
 ok, worst = True, 0.0
 # repeated calls exercise buffer reuse across propagations; odd K with a DIFFERENT H0 per call is the
 # write-after-read hazard of the peer-memory push: a fast rank must not overwrite halo rows
