@@ -63,8 +63,10 @@ static int propagate_impl(const gnntf_csr_t* A_k, int n_adj, int K, const float*
         int rc = validate_csr(&A_k[0]);
         if (rc != GNNTF_OK) return rc;
         bool taken = false;
+#ifndef GNNTF_NO_AUTO_CLUSTER  // (A/B builds only: scripts/cluster_ab.py compares against a library without this path)
         rc = appnp_cluster_propagate(&A_k[0], H0, H_out, ld, F, alpha, K, 0, 0, st, &taken);
         if (rc != GNNTF_OK || taken) return rc;
+#endif
         rc = spmm_persistent_propagate(&A_k[0], H0, H_out, scratch, ld, F, alpha, K, st, &taken);
         if (rc != GNNTF_OK || taken) return rc;
     }

@@ -173,6 +173,14 @@ def split_by_column(row_ptr, col_idx, val, n_local):
     return own, halo, rows
 
 
+def global_columns(plan, own_col, halo_col):
+    """Column ids of the two parts of :func:`split_by_column` in GLOBAL numbering (the all-gather buffer layout of
+    the copy-engine exchange: every rank's buffer holds all rows, its own block at rows [lo, hi))."""
+    own = (own_col.long() + plan.lo).to(torch.int32).contiguous()
+    halo = plan.halo_cols[halo_col.long() - plan.n_local].to(torch.int32).contiguous()
+    return own, halo
+
+
 def sub_csr(row_ptr, col_idx, val, rows):
     """Compact CSR of a row subset (``rows`` int32 ascending): (row_ptr, col_idx, val)."""
     dev = row_ptr.device
@@ -277,8 +285,7 @@ class ShardedPropagator:
         self.n_total = int(p.bounds[-1])
         self.row0 = p.lo if self.copy else 0          # first owned row inside the feature buffers
         if self.copy:
-            o_col = (o_col + p.lo).to(torch.int32).contiguous()
-            h_col = p.halo_cols[h_col.long() - self.n_local].to(torch.int32).contiguous()
+            o_col, h_col = global_columns(p, o_col, h_col)
         self.owned, self.owned_val = CsrStructure(self.n_local, o_rp, o_col, None), o_val
         self.halo_part, self.halo_val = CsrStructure(int(h_rows.numel()), h_rp, h_col, None), h_val
         self.halo_part.row_map = h_rows
@@ -707,35 +714,81 @@ class ShardedPropagator:
         self._compute(part, src, dst, None)
         return dst[:self.n_local, :part["F"]]
 
-    def propagate_host_timed(self, H0_host, alpha, iterations, reps=3):
-        """End-to-end: this shard's rows of H0 in pinned host memory -> device, K steps, result shard -> host.
-        Returns the timing and the host result of the last repetition (for the caller's parity check)."""
-        import time
-        host_in = H0_host if H0_host.is_pinned() else H0_host.pin_memory()
-        host_out = torch.empty_like(host_in).pin_memory()
-        dev_in = torch.empty((self.n_local, self.F), dtype=torch.float32, device=self.H0.device)
+    def propagate_host_batched(self, host_ins, host_outs, alpha, iterations, work=None):
+        """End-to-end for a sequence of HOST inputs (this rank's rows, pinned): the upload of input b+1 and the
+        read-back of result b-1 overlap the K steps of input b (three streams, two device slots; the result is
+        staged out of the ping-pong buffer so that the next propagation may overwrite it).  ``host_outs[b]``
+        receives the result of ``host_ins[b]``; entries may repeat.  Synchronises before returning."""
+        dev = self.H0.device
+        if work is None:
+            work = [torch.empty((self.n_local, self.F), dtype=torch.float32, device=dev) for _ in range(4)]
+        dev_in, stage = work[:2], work[2:4]
+        if getattr(self, "_io_streams", None) is None:
+            self._io_streams = (torch.cuda.Stream(), torch.cuda.Stream())
+        up, down = self._io_streams
+        cur = torch.cuda.current_stream()
+        start = torch.cuda.Event()
+        start.record(cur)
+        up.wait_event(start)
+        down.wait_event(start)
+        ev_comp, ev_out = [None, None], [None, None]
+        for b, (h_in, h_out) in enumerate(zip(host_ins, host_outs)):
+            s = b & 1
+            with torch.cuda.stream(up):
+                if ev_comp[s] is not None:
+                    up.wait_event(ev_comp[s])              # propagation b-2 has consumed this slot's input
+                dev_in[s].copy_(h_in, non_blocking=True)
+                ev_in = torch.cuda.Event()
+                ev_in.record(up)
+            cur.wait_event(ev_in)
+            if ev_out[s] is not None:
+                cur.wait_event(ev_out[s])                  # read-back b-2 has drained this slot's staging buffer
+            stage[s].copy_(self.propagate(dev_in[s], alpha, iterations))
+            ev_comp[s] = torch.cuda.Event()
+            ev_comp[s].record(cur)
+            with torch.cuda.stream(down):
+                down.wait_event(ev_comp[s])
+                h_out.copy_(stage[s], non_blocking=True)
+                ev_out[s] = torch.cuda.Event()
+                ev_out[s].record(down)
+        for ev in ev_out:
+            if ev is not None:
+                cur.wait_event(ev)
+        torch.cuda.synchronize()
 
-        def once():
-            dev_in.copy_(host_in, non_blocking=True)
-            out = self.propagate(dev_in, alpha, iterations)
-            host_out.copy_(out, non_blocking=True)
-            torch.cuda.synchronize()
-        once()
+    def propagate_host_timed(self, H0_host, alpha, iterations, reps=3):
+        """End-to-end timing: this shard's rows of H0 in pinned host memory -> device, K steps, result shard ->
+        host, for ``reps`` consecutive steps pipelined by :meth:`propagate_host_batched` (every step moves its own
+        input and its own result across PCIe inside the timed region).  Also times ONE un-pipelined call.
+        Returns the timings and the host result of the last step (for the caller's parity check)."""
+        import time
+        dev = self.H0.device
+        host_in = H0_host if H0_host.is_pinned() else H0_host.pin_memory()
+        outs = [torch.empty_like(host_in).pin_memory() for _ in range(2)]
+        work = [torch.empty((self.n_local, self.F), dtype=torch.float32, device=dev) for _ in range(4)]
         multi = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+
+        def timed(n):
+            if multi:
+                dist.barrier()                       # timing spans ALL ranks (every column group)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            self.propagate_host_batched([host_in] * n, [outs[b & 1] for b in range(n)], alpha, iterations, work=work)
+            if multi:
+                dist.barrier()
+            sec = (time.perf_counter() - t0) / n
+            t = torch.tensor([sec], dtype=torch.float64, device=dev)
+            if multi:
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item())
+        timed(2)                                     # warm-up (CUDA-graph capture of the propagation included)
+        single = timed(1)
+        sec = timed(max(1, reps))
+        nbytes = torch.tensor([float(host_in.numel() * 4)], dtype=torch.float64, device=dev)
         if multi:
-            dist.barrier()                       # timing spans ALL ranks (every column group)
-        t0 = time.perf_counter()
-        for _ in range(reps):
-            once()
-        if multi:
-            dist.barrier()
-        sec = (time.perf_counter() - t0) / reps
-        t = torch.tensor([sec], dtype=torch.float64, device=self.H0.device)
-        nbytes = torch.tensor([float(host_in.numel() * 4)], dtype=torch.float64, device=self.H0.device)
-        if multi:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
             dist.all_reduce(nbytes, op=dist.ReduceOp.SUM)
-        return {"seconds": float(t.item()), "h2d": int(nbytes.item()), "d2h": int(nbytes.item()), "host_out": host_out}
+        return {"seconds": sec, "single_call_seconds": single, "h2d": int(nbytes.item()), "d2h": int(nbytes.item()),
+                "host_out": outs[(max(1, reps) - 1) & 1]}
 
 
 # ----------------------------------------------------------------------------------------------

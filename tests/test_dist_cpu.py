@@ -71,6 +71,35 @@ def _worker(rank, world, port, n, edges, F, K, alpha, out_dir):
         srp, scol, sval = gdist.sub_csr(plan.row_ptr, plan.col_idx, plan.val, plan.boundary_rows)
         for i, r in enumerate(plan.boundary_rows.tolist()[:20]):
             assert np.array_equal(scol[srp[i]:srp[i + 1]].numpy(), col[rp[r]:rp[r + 1]])
+        # all-gather layout of the copy-engine exchange: columns back in global numbering, every rank holds all rows,
+        # per step an all-gather of the row blocks, then the owned-column pass and the halo-column pass
+        (o_rp, o_col, o_val), (h_rp, h_col, h_val), h_rows = gdist.split_by_column(plan.row_ptr, plan.col_idx, plan.val, plan.n_local)
+        og, hg = gdist.global_columns(plan, o_col, h_col)
+        assert og.numel() + hg.numel() == col.size
+        if og.numel():
+            assert int(og.min()) >= plan.lo and int(og.max()) < plan.hi
+        if hg.numel():
+            assert bool(((hg < plan.lo) | (hg >= plan.hi)).all())
+        full_cols = torch.from_numpy(col_idx[row_ptr[plan.lo]:row_ptr[plan.hi]].astype(np.int64))
+        merged = torch.where(plan.col_idx.long() < plan.n_local, plan.col_idx.long() + plan.lo,
+                             plan.halo_cols[(plan.col_idx.long() - plan.n_local).clamp(min=0)] if plan.n_halo else plan.col_idx.long())
+        assert torch.equal(merged, full_cols)
+        o_rows = np.repeat(np.arange(plan.n_local), np.diff(o_rp.numpy()))
+        h_rows_e = np.repeat(h_rows.numpy(), np.diff(h_rp.numpy()))
+        sizes = [plan.bounds[r + 1] - plan.bounds[r] for r in range(world)]
+        H = H0.copy()
+        for _ in range(K):
+            blocks = [torch.empty((max(sizes), F), dtype=torch.float32) for _ in sizes]   # gloo gathers equal shapes
+            mine = torch.zeros((max(sizes), F), dtype=torch.float32)
+            mine[:plan.n_local] = torch.from_numpy(H)
+            dist.all_gather(blocks, mine)
+            full = torch.cat([b[:sz] for b, sz in zip(blocks, sizes)]).numpy()
+            P = oracle.spmm_coo(np.stack([o_rows, og.numpy().astype(np.int64)], 1), o_val.numpy(), full, n_rows=plan.n_local)
+            if hg.numel():
+                P = P + oracle.spmm_coo(np.stack([h_rows_e.astype(np.int64), hg.numpy().astype(np.int64)], 1), h_val.numpy(), full,
+                                        n_rows=plan.n_local)
+            H = P * np.float32(1 - alpha) + H0 * np.float32(alpha)
+        oracle.assert_close(H, expect, what=f"rank {rank} shard, all-gather layout", floor=oracle.FLOOR_REORDERED)
         np.save(os.path.join(out_dir, f"ok_{rank}.npy"), np.array([plan.n_local, plan.n_halo]))
     finally:
         dist.destroy_process_group()

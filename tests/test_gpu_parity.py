@@ -636,6 +636,26 @@ def test_sharded_push_loop_with_emulated_peers(world, F, K, copy):
         p.close()
 
 
+def test_sharded_host_pipeline_world1_matches_device_run():
+    """ShardedPropagator.propagate_host_batched / propagate_host_timed (upload, K steps and read-back of
+    consecutive inputs on three streams): every host result equals the device-side propagation of its input."""
+    gnntf = _gnntf()
+    from gnntf import dist as gdist
+    n, edges = synthetic.shaped_edges("arxiv", seed=0, device="cuda", scale=0.2)
+    adj = gnntf.edges2adj(edges, None, n)
+    A = adj.normalized("symmetric")
+    prop = gdist.ShardedPropagator(adj, A, 40, 0, 1)
+    ins = [torch.randn((n, 40)).pin_memory() for _ in range(3)]
+    seq = [ins[b % 3] for b in range(5)]
+    outs = [torch.empty((n, 40)).pin_memory() for _ in range(5)]
+    prop.propagate_host_batched(seq, outs, 0.1, 10)
+    for h_in, h_out in zip(seq, outs):
+        assert torch.equal(h_out, gnntf.appnp_propagate(A, h_in.cuda(), 0.1, 10).cpu())
+    rec = prop.propagate_host_timed(ins[1], 0.1, 10, reps=3)
+    assert torch.equal(rec["host_out"], gnntf.appnp_propagate(A, ins[1].cuda(), 0.1, 10).cpu())
+    assert rec["seconds"] > 0 and rec["single_call_seconds"] > 0 and rec["h2d"] == n * 40 * 4
+
+
 def test_sharded_propagator_column_halves_world1_matches():
     """The two-half software pipeline (used when world > 1) on one rank: same result as one chain."""
     gnntf = _gnntf()
