@@ -59,14 +59,13 @@ static int propagate_impl(const gnntf_csr_t* A_k, int n_adj, int K, const float*
         return GNNTF_OK;
     }
     if (K > 1 && scratch == nullptr && n > 0 && F > 0) return GNNTF_E_NULL;
-    if (n_adj == 1 && K > 1) {  // launch-bound shapes: all K steps in one cluster launch / one cooperative launch
+    if (n_adj == 1 && K > 1) {  // launch-bound shapes: all K steps in one cooperative launch
+        // (the cluster-resident form, gnntf_appnp_propagate_cluster_f32, is NOT taken here: with the wide lane groups
+        // the cooperative kernel runs Cora in 42.5 us, the cluster kernel in 43.1 us, and everything larger is
+        // slower through DSMEM than through L2 — profiles/r2/17)
         int rc = validate_csr(&A_k[0]);
         if (rc != GNNTF_OK) return rc;
         bool taken = false;
-#ifndef GNNTF_NO_AUTO_CLUSTER  // (A/B builds only: scripts/cluster_ab.py compares against a library without this path)
-        rc = appnp_cluster_propagate(&A_k[0], H0, H_out, ld, F, alpha, K, 0, 0, st, &taken);
-        if (rc != GNNTF_OK || taken) return rc;
-#endif
         rc = spmm_persistent_propagate(&A_k[0], H0, H_out, scratch, ld, F, alpha, K, st, &taken);
         if (rc != GNNTF_OK || taken) return rc;
     }

@@ -240,8 +240,8 @@ int appnp_cluster_propagate(const gnntf_csr_t* A, const float* H0, float* H_out,
     int C = cluster_size;
     if (C == 0) {
         // Measured (profiles/r2/17): gathers of 16-32 bytes through DSMEM run at only ~5 bytes per clock per SM, so
-        // the resident form beats the cooperative L2 form only for Cora-sized problems spread over 16 CTAs
-        // (K=10, F=8: 43 us vs 57 us); PubMed-sized ones are 3x slower than through L2.  Everything else declines.
+        // the only shapes where the resident form is competitive are Cora-sized ones spread over 16 CTAs
+        // (K=10, F=8: 43 us); PubMed-sized ones are 3x slower than through L2.  Everything else declines.
         if (A->n_rows > 4096 || group > 2) return GNNTF_OK;
         L = plan_layout(A->n_rows, A->nnz, P, 16);
         if (L.smem == 0 || !L.h0_resident || (int64_t)L.cap * 16 < A->nnz + A->nnz / 4) return GNNTF_OK;

@@ -777,7 +777,7 @@ static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 
 // issues K ordinary launches).
 template <int GROUP>
 static int try_persistent(const gnntf_csr_t* A, const float* H0, float* H_out, float* scratch, int64_t ld,
-                          const Epilogue& epi, int K, cudaStream_t st, bool* taken) {
+                          const Epilogue& epi, int K, cudaStream_t st, bool* taken, bool single_round_only = false) {
     constexpr int THREADS = 256, MINB = 5;
     constexpr int UNROLL = (GROUP >= 8) ? 8 : 4;
     constexpr int NG = 32 / GROUP;
@@ -796,6 +796,7 @@ static int try_persistent(const gnntf_csr_t* A, const float* H0, float* H_out, f
     while (rounds < 32 / NG && ceil_div(A->n_rows, (int64_t)(THREADS / 32) * NG * rounds) * gy > slots) rounds *= 2;
     const int64_t gx = ceil_div(A->n_rows, (int64_t)(THREADS / 32) * NG * rounds);
     if (slots == 0 || gx * gy > slots) return GNNTF_OK;
+    if (single_round_only && rounds > 1) return GNNTF_OK;
     const int* row_ptr = A->row_ptr;
     const int* col_idx = A->col_idx;
     const float* val = A->val;
@@ -822,7 +823,24 @@ int spmm_persistent_propagate(const gnntf_csr_t* A, const float* H0, float* H_ou
     e.ldc = ld;
     e.F = (int)F;
     const int64_t slots = F / 4;
-    if (slots <= 4) return try_persistent<4>(A, H0, H_out, scratch, ld, e, K, st, taken);
+    // These shapes are bound by latency, not by lanes: a lane group WIDER than the row needs (idle lanes) puts fewer
+    // rows on a warp and spreads the graph over more SMs — Cora, F = 8: 43 CTAs with 4-lane groups, 339 with a warp
+    // per row (measured: the F = 64 mapping ran the same graph in 42 us where the F = 8 mapping took 55 us).
+    // Taken while every warp still needs a single round and the grid stays co-resident.
+    int rc = GNNTF_OK;
+    if (slots <= 16) {
+        rc = try_persistent<32>(A, H0, H_out, scratch, ld, e, K, st, taken, true);
+        if (rc != GNNTF_OK || *taken) return rc;
+    }
+    if (slots <= 8) {
+        rc = try_persistent<16>(A, H0, H_out, scratch, ld, e, K, st, taken, true);
+        if (rc != GNNTF_OK || *taken) return rc;
+    }
+    if (slots <= 4) {
+        rc = try_persistent<8>(A, H0, H_out, scratch, ld, e, K, st, taken, true);
+        if (rc != GNNTF_OK || *taken) return rc;
+        return try_persistent<4>(A, H0, H_out, scratch, ld, e, K, st, taken);
+    }
     if (slots <= 8) return try_persistent<8>(A, H0, H_out, scratch, ld, e, K, st, taken);
     if (slots <= 16) return try_persistent<16>(A, H0, H_out, scratch, ld, e, K, st, taken);
     return try_persistent<32>(A, H0, H_out, scratch, ld, e, K, st, taken);

@@ -194,8 +194,9 @@ def propagate_raw(adjs, H0, alpha, K, out=None, scratch=None):
 
 def propagate_cluster_raw(adj, H0, alpha, K, cluster_size=0, threads=0, out=None):
     """The K steps in ONE thread-block-cluster launch with the graph and the features resident in the
-    cluster's shared memory (gnntf_appnp_propagate_cluster_f32; Cora / PubMed-sized problems only — the general
-    entry takes this path by itself when the shape qualifies).  Returns None when the shape does not qualify."""
+    cluster's shared memory (gnntf_appnp_propagate_cluster_f32; Cora / PubMed-sized problems only).  An explicit
+    alternative: the general entry keeps the cooperative launch, which measured as fast or faster.
+    Returns None when the shape does not qualify."""
     L = nat.lib()
     F, ld = H0.shape[1], _ld(H0)
     out = out if out is not None else torch.empty_like(H0)

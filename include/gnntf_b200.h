@@ -183,8 +183,8 @@ int gnntf_appnp_propagate_f32(const gnntf_csr_t* A, const float* H0, float* H_ou
  * rows through distributed shared memory and meet at a hardware cluster barrier between steps — global
  * memory is read once and written once.  For graphs the size of Cora / PubMed (n_rows*F*12 bytes plus the
  * CSR must fit the cluster's shared memory, F <= 128, F % 4 == 0, ld % 4 == 0, no split rows, 16-byte
- * aligned bases); results are bit-identical to gnntf_appnp_propagate_f32, which takes this path by
- * itself when the shape qualifies.  cluster_size: 0 = choose, else 1, 2, 4, 8 or 16 CTAs; threads: 0 = choose,
+ * aligned bases); results are bit-identical to gnntf_appnp_propagate_f32.  An explicit alternative, not
+ * a default: measured no faster than the cooperative launch the general entry uses.  cluster_size: 0 = choose, else 1, 2, 4, 8 or 16 CTAs; threads: 0 = choose,
  * else 512 or 1024 per CTA.
  * Returns GNNTF_E_SHAPE when the shape does not qualify (nothing was enqueued).  No scratch needed. */
 int gnntf_appnp_propagate_cluster_f32(const gnntf_csr_t* A, const float* H0, float* H_out, int64_t ld,
