@@ -111,6 +111,7 @@ for F in widths:
                               edge_features_per_s=nnz * F / (med * 1e-3), algorithmic_GBs=gb / (med * 1e-3),
                               frac_of_measured_peak=gb / (med * 1e-3) / (PEAK * world), csr_build_ms=build_ms,
                               max_degree=max_degree, long_rows=adj.csr.n_long, pieces=adj.csr.n_chunks,
+                              exchange=("none" if world == 1 else ("copy-engine all-gather" if prop.copy else "push kernel")),
                               max_halo_rows=int(halo.item()), check_max_rel_err=float(err.item()),
                               peak_mem_GB=torch.cuda.max_memory_allocated() / 1e9)), flush=True)
     if world > 1:
