@@ -358,8 +358,8 @@ def gpu_arm(args):
         result = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic", "config": dict(config_dict(args, n, E, nnz, F), padded_features=F_run,
-                           sharding=(sharding if world > 1 else "none")),
+            "dtype": "f32", "data": "synthetic", "config": config_dict(args, n, E, nnz, F),   # same keys and values as --impl reference
+            "layout": {"padded_features": F_run, "sharding": (sharding if world > 1 else "none")},
             "propagation_ms": {"mean": ms_per_step, "min": float(per_step_ms.min().item()),
                                "median": float(per_step_ms.median().item())},
             "clocks": clocks, "gpu_launches": launches_per_step * args.steps,
@@ -372,7 +372,7 @@ def gpu_arm(args):
             "csr_build_ms": build_s * 1e3,
         }
         if world > 1:
-            result["config"]["k_step_launch"] = ("one CUDA graph replay per propagation (both streams captured)"
+            result["layout"]["k_step_launch"] = ("one CUDA graph replay per propagation (both streams captured)"
                                                  if any(isinstance(v, tuple) for v in prop._graphs.values()) else "launched step by step from the host")
             result["roofline"]["note"] += f"; aggregate over {world} GPUs, peak is per-GPU x {world}"
             result["roofline"]["peak"] = hbm_peak * world
