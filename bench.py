@@ -365,7 +365,7 @@ def gpu_arm(args):
             "clocks": clocks, "gpu_launches": launches_per_step * args.steps,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
                          "traffic": measured_traffic(args, F) if world == 1 else None, "peak_source": peak_src, "frac_of_nominal_8TBs": achieved / 8000.0,
-                         "kernel": "fused APPNP step (spmm_rows_kernel + long-row pieces/reduce)",
+                         "kernel": "fused APPNP step (spmm_rows4_kernel, long-row pieces in its grid, + spmm_long_reduce_kernel)",
                          "algorithmic_bytes_per_launch": bstep,
                          "avg_launch_ms": ms_per_step / K_ITER,
                          "note": "achieved = B_step / (timed region / (steps*K)); B_step = 8*nnz + 4*(N+1) + 12*N*F"},
