@@ -54,6 +54,16 @@ def test_argument_errors_return_codes_not_exceptions():
     assert lib.gnntf_csr_build_ws_bytes(-1, 0, 0, 0, ctypes.byref(ctypes.c_size_t())) == -2
     assert lib.gnntf_csr_build_ws_bytes(10, 2 ** 31, 0, 0, ctypes.byref(ctypes.c_size_t())) == -2
     assert lib.gnntf_halo_pack_f32(null, 2, null, 3, null, 4, 4, null) == -2                       # ld < F
+    # entry points added in round 2: argument errors come back before any CUDA call
+    assert lib.gnntf_appnp_propagate_host_batched_f32(None, null, null, 2, null, 4, 4, 0.1, 10, null) == -1
+    csr.n_rows, csr.nnz = 5, 3
+    assert lib.gnntf_appnp_propagate_host_batched_f32(ctypes.byref(csr), null, null, -1, null, 4, 4, 0.1, 10, null) == -2
+    assert lib.gnntf_appnp_propagate_host_batched_f32(ctypes.byref(csr), null, null, 0, null, 4, 4, 0.1, 10, null) == 0   # nothing to do
+    assert lib.gnntf_appnp_propagate_host_batched_f32(ctypes.byref(csr), null, null, 2, null, 4, 4, 0.1, 10, null) == -1
+    assert lib.gnntf_appnp_propagate_cluster_f32(None, null, null, 4, 4, 0.1, 10, 0, 0, null) == -1
+    assert lib.gnntf_peer_copy_signal(null, null, 16, null, null, null) == -1
+    assert lib.gnntf_peer_copy_signal(null, null, 0, null, null, null) == 0                        # no rows, no flag: nothing enqueued
+    assert b"shape" in lib.gnntf_status_str(-6)
     with pytest.raises(Exception, match="Invalid matrix normalization"):
         _native.check(-3)
 

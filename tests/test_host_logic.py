@@ -115,3 +115,17 @@ def test_reorder_rank_uniformisation_is_a_permutation():
     ranks, order = _uniformize(theta)
     assert order.tolist() == [4, 1, 3, 0, 2]
     assert torch.allclose(ranks, torch.tensor([3, 1, 4, 2, 0], dtype=torch.float32) * (2 * np.pi / 5))
+
+
+def test_pitch_for_row_pitch_rule():
+    """ops.pitch_for: the leading dimension of sharded feature buffers — rounded up to 32 floats only when that
+    saves >= 10 % of the 128-byte lines a row gather touches and costs <= 35 % more memory."""
+    from gnntf.ops import pitch_for
+    assert pitch_for(52) == 64          # 208-byte rows: 2.5 lines on average at a dense pitch, 2 at 256 bytes
+    assert pitch_for(100) == 100        # 400-byte rows touch 4 lines either way
+    assert pitch_for(48) == 48 and pitch_for(40) == 40 and pitch_for(16) == 16
+    assert pitch_for(64) == 64 and pitch_for(128) == 128 and pitch_for(256) == 256
+    assert pitch_for(7) == 8 and pitch_for(47) == 48      # class widths: padded to float4 first
+    for F in range(1, 300):
+        ld = pitch_for(F)
+        assert ld >= F and ld % 4 == 0 and ld <= 1.35 * ((F + 3) // 4 * 4) + 1e-9
